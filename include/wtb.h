@@ -1,0 +1,133 @@
+/*
+ * wtb.h -- C ABI of libwavelet_sm100a.so, the B200-native wavelet engine.
+ *
+ * The reference (o-nate/wavelet-transformer) is pure Python and has no FFI
+ * layer; its seam is the `import pycwt as wavelet` / `import pywt` lines of
+ * src/cwt.py:19, src/wct.py:14, src/xwt.py:12, src/dwt.py:14, src/modwt.py:14.
+ * Each entry point below replaces one library call made through that seam and
+ * cites it.  Host side: NumPy -> ctypes (wavelet_transformer_b200/_shim.py).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative WTB_E* code on failure;
+ *    wtb_last_error() returns a thread-local message for the last failure.
+ *  - all arrays are C-contiguous; "real" is float (default) or double (WTB_F64).
+ *  - complex planes are interleaved (re, im) pairs of "real".
+ *  - the caller owns every buffer; the library keeps no caller pointer past
+ *    return.  Without WTB_DEVICE_PTRS buffers are host memory and the call is
+ *    synchronous (copies inside).  With WTB_DEVICE_PTRS buffers are device
+ *    memory on the current device and the call only enqueues work on `stream`
+ *    (a cudaStream_t, NULL = default stream).
+ *  - there is no CPU fallback: without a usable sm_100 device calls fail.
+ */
+#ifndef WTB_H
+#define WTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WTB_OK            0
+#define WTB_EINVAL       -1   /* bad argument */
+#define WTB_ECUDA        -2   /* CUDA runtime error (message has the detail) */
+#define WTB_EUNSUPPORTED -3   /* size / mode outside what the kernels cover */
+#define WTB_ENODEVICE    -4   /* no CUDA device, or not sm_100 */
+
+#define WTB_F64          (1 << 0)  /* compute and I/O in double precision */
+#define WTB_DEVICE_PTRS  (1 << 1)  /* data pointers are device pointers; async on stream */
+#define WTB_COI_MASK     (1 << 2)  /* cwt power: write NaN outside the cone of influence */
+#define WTB_NOISE_WHITE  (1 << 3)  /* Monte Carlo surrogates: white instead of AR(1) */
+#define WTB_GENERIC_ONLY (1 << 4)  /* force the generic (any pow2 N) kernels; testing */
+
+#define WTB_NBINS 1000             /* pycwt wct_significance: nbins = 1000 */
+
+/* ---- runtime ------------------------------------------------------------ */
+int  wtb_version(void);
+int  wtb_device_count(void);
+/* Bind the calling process to `device` (one process per GPU) and verify it is
+ * compute capability 10.x. */
+int  wtb_init(int device);
+void wtb_shutdown(void);
+const char *wtb_last_error(void);
+
+/* ---- CWT: replaces pycwt.cwt (src/cwt.py:110) + |W|^2 (src/cwt.py:114) ---- */
+/* Scales, Fourier frequencies and cone of influence exactly as pycwt.cwt
+ * forms them.  s0 == -1 and J == -1 select pycwt's defaults; *J_out gets the
+ * resolved J (S = J+1 scales).  Any output pointer may be NULL. */
+int wtb_cwt_axes(int n0, double dt, double dj, double s0, int J, double f0,
+                 int *J_out, double *scales, double *freqs, double *coi);
+
+/* Batched Morlet CWT.  x: [batch, n0] real.  nfft: FFT length (power of two
+ * >= n0; pycwt's scipy.fftpack path pads to 2^ceil(log2 n0)).  Outputs (either
+ * may be NULL): power_out [batch, S, n0] real = |W|^2; coef_out [batch, S, n0]
+ * complex = W.  S = J+1 with scales s0*2^(j*dj).  No normalisation of x. */
+int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft,
+                   double dt, double dj, double s0, int J, double f0, int flags,
+                   void *power_out, void *coef_out, void *stream);
+
+/* ---- XWT / WCT: replaces pycwt.xwt (src/xwt.py:93) and pycwt.wct
+ * (src/wct.py:106, src/xwt.py:122) minus the host-side normalisation ------- */
+/* y1, y2: [batch, n0] real (already normalised by the caller).  Outputs (any
+ * may be NULL): wct_out [batch,S,n0] real = |S12|^2/(S1*S2); phase_out
+ * [batch,S,n0] real = angle(W1*conj(W2)); w12_out [batch,S,n0] complex. */
+int wtb_xwt_wct(const void *y1, const void *y2, int64_t batch, int n0, int nfft,
+                double dt, double dj, double s0, int J, double f0, int flags,
+                void *wct_out, void *phase_out, void *w12_out, void *stream);
+
+/* ---- Monte Carlo coherence significance: replaces pycwt.wct_significance -- */
+/* Surrogate length N = ceil(6*s0*2^(J*dj)/dt) and the largest scale index
+ * with any point inside the reliable region (pycwt's `maxscale`). */
+int wtb_wct_mc_geometry(double dt, double dj, double s0, int J, double f0,
+                        int *nsurr, int *maxscale);
+
+/* Accumulate per-scale coherence histograms of `mc_count` realisations whose
+ * GLOBAL indices are mc_first .. mc_first+mc_count-1 (the Philox stream is
+ * keyed by the global index, so any partition over GPUs sums to the same
+ * histogram).  surrogates: NULL -> AR(1) (or white) noise generated on device
+ * from `seed`; else [mc_count, 2, nsurr] real ready-made series (host-injected
+ * parity mode).  hist: [S, WTB_NBINS] uint64, ADDED to (caller zeroes). */
+int wtb_wct_mc_hist(double a1, double a2, double dt, double dj, double s0, int J,
+                    double f0, int64_t mc_first, int64_t mc_count, uint64_t seed,
+                    const void *surrogates, int flags, uint64_t *hist, void *stream);
+
+/* Percentile step (host arithmetic, tiny): sig95[s] for s < maxscale from the
+ * histogram, NaN for the remaining rows that have reliable points. */
+int wtb_wct_sig_from_hist(const uint64_t *hist, int S, int maxscale, double level,
+                          const uint8_t *row_has_points, double *sig95);
+
+/* Device AR(1) surrogates only (for distribution tests): out [count, 2, nsurr]. */
+int wtb_rednoise(double a1, double a2, int nsurr, int64_t first, int64_t count,
+                 uint64_t seed, int flags, void *out, void *stream);
+
+/* ---- MODWT: replaces src/modwt.py:126 modwt, :147 imodwt, :163 modwtmra --- */
+/* g = dec_lo, h = dec_hi (pywt.Wavelet taps, length L, NOT yet divided by
+ * sqrt 2).  x: [batch, n]; w: [batch, J+1, n] rows w_1..w_J, v_J. */
+int wtb_modwt(const void *x, int64_t batch, int n, const double *g, const double *h,
+              int L, int J, int flags, void *w_out, void *stream);
+int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, const double *h,
+               int L, int J, int flags, void *x_out, void *stream);
+/* filt: [J+1, n] periodised equivalent filters (host-built, see
+ * modwt.py:56-83); out[b,j,t] = sum_l filt[j,l] * w[b,j,(t+l) mod n]. */
+int wtb_modwtmra(const void *w, int64_t batch, int n, const double *filt, int J,
+                 int flags, void *out, void *stream);
+
+/* ---- DWT: replaces pywt.wavedec / pywt.waverec (src/dwt.py:104,71,120) ---- */
+/* lens: [level+1] lengths of cA_L, cD_L, ..., cD_1 for symmetric mode. */
+int wtb_dwt_coeff_lens(int n, int L, int level, int *lens);
+int wtb_dwt_max_level(int n, int L);
+/* coeffs: [batch, sum(lens)] packed in pywt order cA_L | cD_L | ... | cD_1. */
+int wtb_wavedec(const void *x, int64_t batch, int n, const double *dec_lo,
+                const double *dec_hi, int L, int level, int flags, void *coeffs,
+                void *stream);
+/* lens as produced by wtb_dwt_coeff_lens (or any consistent pywt-style list);
+ * x_out: [batch, n_out] with n_out = wtb_waverec_len(lens, level, L). */
+int wtb_waverec_len(const int *lens, int level, int L);
+int wtb_waverec(const void *coeffs, int64_t batch, const int *lens, int level,
+                const double *rec_lo, const double *rec_hi, int L, int flags,
+                void *x_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WTB_H */

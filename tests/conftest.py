@@ -1,0 +1,51 @@
+"""Shared fixtures.  `-m gpu` tests call the CUDA library through the C ABI and
+are checked against the CPU oracle; everything else runs without a GPU."""
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) and the built libwavelet_sm100a.so")
+
+
+@pytest.fixture(scope="session")
+def series():
+    """sample_data/*.csv value columns (copied by tests/golden/make_golden.py)."""
+    return dict(np.load(GOLDEN / "sample_series.npz"))
+
+
+@pytest.fixture(scope="session")
+def modwt_golden():
+    return dict(np.load(GOLDEN / "modwt_reference.npz"))
+
+
+@pytest.fixture(scope="session")
+def helpers_golden():
+    return dict(np.load(GOLDEN / "helpers_reference.npz"))
+
+
+@pytest.fixture(scope="session")
+def shim():
+    """The ctypes binding, bound to cuda:0.  GPU tests fail (not skip) when the
+    library is missing: a silent fallback would void the parity claim."""
+    from wavelet_transformer_b200 import _shim
+    _shim.init(0)
+    return _shim
+
+
+def normwise_close(a, b, tol):
+    """FP32 gate of BASELINE.md: |a-b| <= tol*|b| + tol*max|b| over the plane."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    bound = tol * np.abs(b) + tol * np.abs(b).max()
+    return bool(np.all(np.abs(a - b) <= bound)), float(np.max(np.abs(a - b) / (np.abs(b).max() + 1e-300)))

@@ -1,0 +1,113 @@
+"""GPU parity: batched Morlet CWT (wtb_cwt_morlet) vs the pycwt oracle.
+
+Tolerances (BASELINE.json north_star): FP64 mode rtol 1e-10 (relative to the
+plane maximum -- FFT round-off is norm-wise), FP32 mode 1e-4 norm-wise."""
+
+import numpy as np
+import pytest
+
+from conftest import normwise_close
+from oracle import pycwt_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+DT = 1 / 12
+
+
+def _oracle_plane(x, dt, dj, s0, J):
+    W = po.cwt(x, dt, dj, s0, J, po.Morlet(6))[0]
+    return W
+
+
+@pytest.mark.parametrize("name,dj,J", [("cpi", 1 / 12, 84), ("inflation", 1 / 12, 84), ("expectation", 1 / 8, -1)])
+def test_cwt_fp64_sample_series(shim, series, name, dj, J):
+    x = series[f"{name}_value"]
+    x = (x - x.mean()) / x.std()
+    W = _oracle_plane(x, DT, dj, 2 * DT, J)
+    power, coef = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=True, want_power=True, want_coef=True)
+    assert coef.shape == W.shape and power.shape == W.shape
+    scale = np.abs(W).max()
+    assert np.abs(coef - W).max() <= 1e-10 * scale
+    assert np.abs(power - np.abs(W) ** 2).max() <= 1e-10 * scale ** 2
+
+
+def test_cwt_fp64_difflog_cpi_cfg1(shim, series):
+    """BASELINE cfg1: the app's fallback series 100*diff(log(cpi)), dj=1/12, s0=2dt, J=84."""
+    x = 100 * np.diff(np.log(series["cpi_value"]))
+    W = _oracle_plane(x, DT, 1 / 12, 2 * DT, 84)
+    power, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, 84, f64=True)
+    assert power.shape == (85, 1345)
+    ref = np.abs(W) ** 2
+    assert np.abs(power - ref).max() <= 1e-10 * ref.max()
+
+
+@pytest.mark.parametrize("n0", [64, 100, 565, 1024, 1346, 2048, 3351, 4096])
+@pytest.mark.parametrize("generic", [False, True])
+def test_cwt_fp32_lengths(shim, n0, generic):
+    rng = np.random.default_rng(n0)
+    x = rng.standard_normal((3, n0))
+    dj, s0 = 1 / 8, 2 * DT
+    power, _ = shim.cwt_morlet(x, DT, dj, s0, -1, f64=False, generic_only=generic)
+    for b in range(3):
+        ref = np.abs(_oracle_plane(x[b], DT, dj, s0, -1)) ** 2
+        ok, err = normwise_close(power[b], ref, 1e-4)
+        assert ok, f"n0={n0} row {b}: normwise err {err:.3e}"
+
+
+def test_cwt_fp32_cfg4_shape(shim):
+    """BASELINE cfg4 shape: N=1024, 120 scales (dj=1/12, s0=2dt, J=119), AR(1) g=0.7."""
+    rng = np.random.default_rng(1234)
+    from scipy.signal import lfilter
+    x = lfilter([1.0], [1.0, -0.7], rng.standard_normal((64, 1024 + 64)), axis=1)[:, 64:]
+    x *= np.sqrt(1 - 0.49)
+    power, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, 119, f64=False)
+    power_g, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, 119, f64=False, generic_only=True)
+    assert power.shape == (64, 120, 1024)
+    for b in range(0, 64, 7):
+        ref = np.abs(_oracle_plane(x[b], DT, 1 / 12, 2 * DT, 119)) ** 2
+        for got in (power[b], power_g[b]):
+            ok, err = normwise_close(got, ref, 1e-4)
+            assert ok, f"row {b}: normwise err {err:.3e}"
+
+
+def test_cwt_batch_equals_single(shim):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((9, 300))
+    pb, _ = shim.cwt_morlet(x, DT, 1 / 4, 2 * DT, -1, f64=True)
+    for b in range(9):
+        p1, _ = shim.cwt_morlet(x[b], DT, 1 / 4, 2 * DT, -1, f64=True)
+        assert np.array_equal(p1, pb[b])
+
+
+def test_cwt_linearity_and_sinusoid_peak(shim):
+    """Size-independent properties: linearity of W and the Fourier-period peak."""
+    n = 4096
+    t = np.arange(n) * DT
+    a, b = np.cos(2 * np.pi * t / 2.0), np.sin(2 * np.pi * t / 7.0)
+    _, Wa = shim.cwt_morlet(a, DT, 1 / 12, 2 * DT, -1, f64=True, want_power=False, want_coef=True)
+    _, Wb = shim.cwt_morlet(b, DT, 1 / 12, 2 * DT, -1, f64=True, want_power=False, want_coef=True)
+    _, Wab = shim.cwt_morlet(2 * a - 3 * b, DT, 1 / 12, 2 * DT, -1, f64=True, want_power=False, want_coef=True)
+    assert np.abs(Wab - (2 * Wa - 3 * Wb)).max() <= 1e-10 * np.abs(Wab).max()
+    _, _, freqs, _ = shim.cwt_axes(n, DT, 1 / 12, 2 * DT, -1)
+    peak = 1 / freqs[(np.abs(Wa) ** 2)[:, n // 2].argmax()]
+    assert abs(np.log2(peak / 2.0)) < 1 / 12
+
+
+def test_cwt_coi_mask(shim):
+    x = np.random.default_rng(3).standard_normal(500)
+    p_mask, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, -1, f64=True, coi_mask=True)
+    p, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, -1, f64=True)
+    _, _, freqs, coi = shim.cwt_axes(500, DT, 1 / 8, 2 * DT, -1)
+    outside = (1 / freqs)[:, None] > coi[None, :]
+    assert np.isnan(p_mask[outside]).all()
+    assert np.array_equal(p_mask[~outside], p[~outside])
+
+
+def test_cwt_rejects_bad_arguments(shim):
+    x = np.zeros(100)
+    with pytest.raises((ValueError, RuntimeError)):
+        shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, -1, nfft=100)      # not a power of two
+    with pytest.raises((ValueError, RuntimeError)):
+        shim.cwt_morlet(x, DT, -1.0, 2 * DT, -1)                 # dj <= 0
+    with pytest.raises((ValueError, RuntimeError)):
+        shim.cwt_morlet(np.zeros(20000), DT, 1 / 8, 2 * DT, -1, f64=True)  # beyond the smem FFT

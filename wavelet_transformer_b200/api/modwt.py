@@ -1,0 +1,90 @@
+"""MODWT entry points -- mirror src/modwt.py:56-194, 232-251.
+
+The reference carries its own circular a-trous arithmetic on
+``scipy.ndimage.convolve1d(mode="wrap")``; here the analysis / synthesis
+pyramids and the MRA correlations run as CUDA kernels, and only the (tiny)
+equivalent-filter construction for the MRA stays on the host.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import numpy.typing as npt
+
+from .. import _shim
+from .. import pywt_compat as pywt
+
+MOTHER = pywt.Wavelet("db4")
+
+
+def _bank(filters):
+    w = filters if hasattr(filters, "dec_lo") else pywt.Wavelet(filters)
+    return np.asarray(w.dec_lo, dtype=float), np.asarray(w.dec_hi, dtype=float)
+
+
+def upArrow_op(li, j):
+    """Insert 2^(j-1)-1 zeros between taps (modwt.py:56-63); j == 0 -> [1]."""
+    if j == 0:
+        return [1]
+    step = 2 ** (j - 1)
+    out = np.zeros(step * (len(li) - 1) + 1)
+    out[::step] = li
+    return out
+
+
+def period_list(li, N):
+    """Periodise a filter to length N (modwt.py:66-78): zero-pad to the next
+    multiple of N -- a whole extra N when already a multiple -- then fold."""
+    f = np.concatenate([np.asarray(li, dtype=float), np.zeros(N - len(li) % N)])
+    return f if f.size < 2 * N else f.reshape(-1, N).sum(axis=0)
+
+
+def modwt(x, filters, level):
+    """Rows w_1..w_J, v_J of the maximal-overlap DWT (modwt.py:126-144)."""
+    g, h = _bank(filters)
+    return np.asarray(_shim.modwt(np.asarray(x, dtype=float), g, h, int(level)), dtype=float)
+
+
+def imodwt(w, filters):
+    """Inverse MODWT (modwt.py:147-160)."""
+    g, h = _bank(filters)
+    return np.asarray(_shim.imodwt(np.asarray(w, dtype=float), g, h), dtype=float)
+
+
+def mra_filters(filters, level, N):
+    """Periodised equivalent filters [h_1 .. h_J, g_J] (modwt.py:172-193)."""
+    g, h = _bank(filters)
+    bank = []
+    g_part = np.array([1.0])
+    for j in range(level):
+        g_part = np.convolve(g_part, upArrow_op(g, j))
+        h_j = np.convolve(g_part, upArrow_op(h, j + 1)) / 2 ** ((j + 1) / 2.0)
+        if j == 0:
+            h_j = h / np.sqrt(2)
+        bank.append(period_list(h_j, N))
+    g_j = np.convolve(g_part, upArrow_op(g, level)) / 2 ** (level / 2.0)
+    bank.append(period_list(g_j, N))
+    return np.vstack(bank)
+
+
+def modwtmra(w, filters):
+    """Multiresolution analysis: details D_1..D_J and smooth S_J (modwt.py:163-194)."""
+    w = np.asarray(w, dtype=float)
+    level, N = w.shape[0] - 1, w.shape[1]
+    return np.asarray(_shim.modwtmra(w, mra_filters(filters, level, N)), dtype=float)
+
+
+def smooth_signal(modwt_coeffs: npt.NDArray, mother_wavelet: str, levels: int):
+    """For l = levels..1 zero detail rows 0..l-1 and invert (modwt.py:232-251)."""
+    out = {}
+    stack = []
+    for l in range(levels, 0, -1):
+        kept = np.array(modwt_coeffs, dtype=float, copy=True)
+        kept[:l] = 0.0
+        out[l] = {"coeffs": kept}
+        stack.append(kept)
+    g, h = _bank(mother_wavelet)
+    signals = _shim.imodwt(np.stack(stack), g, h)  # one batched launch for all levels
+    for i, l in enumerate(range(levels, 0, -1)):
+        out[l]["signal"] = np.asarray(signals[i], dtype=float)
+    return out

@@ -1,0 +1,152 @@
+// Batched Morlet CWT (pycwt.cwt, src/cwt.py:110-114 of the reference):
+//   X = fft(x, nfft);  W[s,:] = ifft(X * sqrt(2*pi*s/dt) * pi^-1/4 * exp(-(s*w-f0)^2/2));
+//   power = |W|^2, truncated to the first n0 samples.
+// Generic kernels (any pow2 nfft, float/double) live here; the FP32 fast path
+// for the headline shape is in cwt_fast.cu and is tried first.
+#include "spectral.cuh"
+
+namespace wtb {
+
+// implemented in cwt_fast.cu; returns 1 when the shape is not covered
+int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
+                 double f0, int flags, float *d_power, cudaStream_t st);
+
+// One CTA = one (series, chunk of scales).  smem: 2 * N complex.
+template <typename T>
+__global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
+                           int chunk, const double *__restrict__ scales, double dt, double f0,
+                           const cplx<T> *__restrict__ tw, T *__restrict__ power,
+                           cplx<T> *__restrict__ coef, int coi_mask, double coi_c, double flambda) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T> *a = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *b = a + N;
+  const int nchunks = (S + chunk - 1) / chunk;
+  const int64_t row = blockIdx.x / nchunks;
+  const int c = blockIdx.x % nchunks;
+  const cplx<T> *xh = xhat + row * N;
+  const int s_end = min(S, (c + 1) * chunk);
+  for (int s = c * chunk; s < s_end; ++s) {
+    const double sc = scales[s];
+    const T s_over_dt = T(sc / dt);
+    // (s * ftfreqs[1] * N)^0.5 * pi^-0.25, times 1/N of the inverse transform
+    const T norm = T(sqrt(2.0 * kPi * sc / dt) * kPiM14 / double(N));
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const T d = morlet_daughter<T>(k, N, s_over_dt, norm, T(f0));
+      cplx<T> v = xh[k];
+      a[k] = mk<T>(v.x * d, v.y * d);
+    }
+    __syncthreads();
+    cplx<T> *r = block_fft<T, +1>(a, b, N, log2N, tw);
+    const int64_t obase = (row * S + s) * (int64_t)n0;
+    const double period = 1.0 / (1.0 / (flambda * sc));
+    for (int t = threadIdx.x; t < n0; t += blockDim.x) {
+      const cplx<T> w = r[t];
+      if (coef) coef[obase + t] = w;
+      if (power) {
+        T p = w.x * w.x + w.y * w.y;
+        if (coi_mask) {
+          const double coi = coi_c * (n0 / 2.0 - fabs(t - (n0 - 1) / 2.0));
+          if (period > coi) p = T(NAN);
+        }
+        power[obase + t] = p;
+      }
+    }
+    __syncthreads();  // r may alias a; next iteration overwrites it
+  }
+}
+
+template <typename T>
+static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, const Axes &ax,
+                      double f0, int flags, T *d_power, cplx<T> *d_coef, cudaStream_t st) {
+  const int S = ax.J + 1;
+  if (sizeof(T) == 4 && d_coef == nullptr && d_power != nullptr && !(flags & WTB_GENERIC_ONLY)) {
+    int rc = cwt_fast_try((const float *)d_x, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
+    if (rc != 1) return rc;
+  }
+  const size_t smem = 2 * sizeof(cplx<T>) * (size_t)N;
+  WTB_REQUIRE(smem <= 227 * 1024, WTB_EUNSUPPORTED,
+              "nfft=%d needs %zu B of shared memory per CTA (limit 227 KB): max nfft is %d for %s",
+              N, smem, sizeof(T) == 4 ? 8192 : 4096, sizeof(T) == 4 ? "float" : "double");
+  const cplx<T> *tw = nullptr;
+  WTB_TRY(twiddles<T>(N, &tw));
+  void *scratch = nullptr;
+  const size_t sc_bytes = ((sizeof(double) * S + 255) / 256) * 256;
+  WTB_TRY(arena_reserve(sc_bytes + sizeof(cplx<T>) * (size_t)batch * N, &scratch));
+  double *d_scales = (double *)scratch;
+  cplx<T> *d_xhat = (cplx<T> *)((char *)scratch + sc_bytes);
+  WTB_CUDA(cudaMemcpyAsync(d_scales, ax.scales.data(), sizeof(double) * S, cudaMemcpyHostToDevice, st));
+  const int log2N = ilog2(N);
+  const int threads = N >= 1024 ? 256 : (N >= 256 ? 128 : 64);
+  WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
+  WTB_CUDA(cudaGetLastError());
+  // enough CTAs to fill the machine for small batches, few forward-FFT re-reads for large ones
+  int chunk = S;
+  const int64_t want = 4LL * sm_count();
+  if (batch < want) chunk = (int)std::max<int64_t>(1, (int64_t)S * batch / want);
+  chunk = std::max(1, std::min(chunk, 16));
+  const int nchunks = (S + chunk - 1) / chunk;
+  WTB_REQUIRE(batch * nchunks < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
+  k_cwt_rows<T><<<(unsigned)(batch * nchunks), threads, smem, st>>>(
+      d_xhat, n0, N, log2N, S, chunk, d_scales, dt, f0, tw, d_power, d_coef,
+      (flags & WTB_COI_MASK) ? 1 : 0, morlet_flambda(f0) / std::sqrt(2.0) * dt, morlet_flambda(f0));
+  WTB_CUDA(cudaGetLastError());
+  return WTB_OK;
+}
+
+template <typename T>
+static int cwt_entry(const void *x, int64_t batch, int n0, int N, double dt, const Axes &ax,
+                     double f0, int flags, void *power_out, void *coef_out, cudaStream_t st) {
+  const int S = ax.J + 1;
+  if (flags & WTB_DEVICE_PTRS)
+    return cwt_device<T>((const T *)x, batch, n0, N, dt, ax, f0, flags, (T *)power_out,
+                         (cplx<T> *)coef_out, st);
+  // host buffers: stream the batch through a bounded staging arena
+  const size_t per_row = sizeof(T) * ((size_t)n0 + (power_out ? (size_t)S * n0 : 0) +
+                                      (coef_out ? 2 * (size_t)S * n0 : 0));
+  const size_t budget = size_t(1) << 30;
+  int64_t rows = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(budget / per_row)));
+  void *stage = nullptr;
+  WTB_TRY(staging_reserve(per_row * rows + 1024, &stage));
+  T *d_x = (T *)stage;
+  size_t off = (sizeof(T) * (size_t)rows * n0 + 255) / 256 * 256;
+  T *d_power = nullptr;
+  cplx<T> *d_coef = nullptr;
+  if (power_out) { d_power = (T *)((char *)stage + off); off += (sizeof(T) * (size_t)rows * S * n0 + 255) / 256 * 256; }
+  if (coef_out) d_coef = (cplx<T> *)((char *)stage + off);
+  for (int64_t b0 = 0; b0 < batch; b0 += rows) {
+    const int64_t nb = std::min(rows, batch - b0);
+    WTB_CUDA(cudaMemcpyAsync(d_x, (const T *)x + b0 * n0, sizeof(T) * nb * n0, cudaMemcpyHostToDevice, st));
+    WTB_TRY(cwt_device<T>(d_x, nb, n0, N, dt, ax, f0, flags, d_power, d_coef, st));
+    if (power_out)
+      WTB_CUDA(cudaMemcpyAsync((T *)power_out + b0 * S * n0, d_power, sizeof(T) * nb * S * n0,
+                               cudaMemcpyDeviceToHost, st));
+    if (coef_out)
+      WTB_CUDA(cudaMemcpyAsync((cplx<T> *)coef_out + b0 * S * n0, d_coef,
+                               sizeof(cplx<T>) * nb * S * n0, cudaMemcpyDeviceToHost, st));
+    WTB_CUDA(cudaStreamSynchronize(st));
+  }
+  return WTB_OK;
+}
+
+}  // namespace wtb
+
+using namespace wtb;
+
+extern "C" int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft, double dt, double dj,
+                              double s0, int J, double f0, int flags, void *power_out,
+                              void *coef_out, void *stream) {
+  WTB_REQUIRE(x && batch >= 0 && n0 > 0, WTB_EINVAL, "wtb_cwt_morlet: bad x/batch/n0");
+  WTB_REQUIRE(power_out || coef_out, WTB_EINVAL, "wtb_cwt_morlet: no output requested");
+  WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
+              "nfft=%d must be a power of two >= n0=%d (pycwt's scipy.fftpack padding rule); "
+              "the un-padded mkl_fft variant is not supported", nfft, n0);
+  WTB_TRY(ensure_device());
+  Axes ax;
+  WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));
+  if (batch == 0) return WTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & WTB_F64) return cwt_entry<double>(x, batch, n0, nfft, dt, ax, f0, flags, power_out, coef_out, st);
+  return cwt_entry<float>(x, batch, n0, nfft, dt, ax, f0, flags, power_out, coef_out, st);
+}

@@ -1,0 +1,469 @@
+// MODWT (reference src/modwt.py:86-194, own arithmetic) and decimated DWT
+// (pywt.wavedec / pywt.waverec, mode='symmetric') filterbank kernels.
+//
+// One CTA owns one series.  The row is staged into shared memory with a 1-D TMA
+// bulk copy (cp.async.bulk + mbarrier) when it is 16-byte aligned, all pyramid
+// levels run out of shared memory, and only coefficients leave the SM.  These
+// paths are HBM-bound: bytes in = N, bytes out = (J+1) N per series.
+#include "common.cuh"
+
+namespace wtb {
+
+constexpr int kMaxTaps = 32;
+struct Taps {
+  int L;
+  double lo[kMaxTaps];  // scaling (g) taps as used by the kernel
+  double hi[kMaxTaps];  // wavelet (h) taps
+};
+
+// ---- TMA 1-D bulk load of `bytes` (multiple of 16, both sides 16B aligned) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Stage `n` elements of a row into shared memory.  All threads call it.
+template <typename T>
+__device__ void stage_row(T *dst, const T *__restrict__ src, int n, uint64_t *bar, uint32_t &phase) {
+  const size_t bytes = sizeof(T) * (size_t)n;
+  const bool tma_ok = (bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && bytes < (1u << 20);
+  if (tma_ok) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)bytes);
+      tma_load_1d(dst, src, (uint32_t)bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  } else {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = src[t];
+    __syncthreads();
+  }
+}
+
+// ---- MODWT analysis: w_j[t] = sum_l h[l] v[(t - 2^(j-1) l) mod N] ---------------------
+template <typename T>
+__global__ void k_modwt(const T *__restrict__ x, int n, int J, Taps taps, T *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  T *v = reinterpret_cast<T *>(smem_raw);
+  T *vn = v + ((n + 3) & ~3);
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  stage_row<T>(v, x + b * n, n, &bar, phase);
+  T *o = out + b * (int64_t)(J + 1) * n;
+  for (int j = 1; j <= J; ++j) {
+    const long long stride = 1LL << (j - 1);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      T w = 0, s = 0;
+      for (int l = 0; l < taps.L; ++l) {
+        int idx = t - (int)((stride * l) % n);
+        if (idx < 0) idx += n;
+        const T val = v[idx];
+        w += T(taps.hi[l]) * val;
+        s += T(taps.lo[l]) * val;
+      }
+      o[(int64_t)(j - 1) * n + t] = w;
+      vn[t] = s;
+    }
+    __syncthreads();
+    T *tmp = v; v = vn; vn = tmp;
+  }
+  for (int t = threadIdx.x; t < n; t += blockDim.x) o[(int64_t)J * n + t] = v[t];
+}
+
+// ---- MODWT synthesis: v_{j-1}[t] = sum_l h[l] w_j[(t+2^(j-1) l) mod N] + g[l] v_j[...] ---
+template <typename T>
+__global__ void k_imodwt(const T *__restrict__ w, int n, int J, Taps taps, T *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int np = (n + 3) & ~3;
+  T *v = reinterpret_cast<T *>(smem_raw);
+  T *vn = v + np;
+  T *wj = vn + np;
+  const int64_t b = blockIdx.x;
+  const T *wb = w + b * (int64_t)(J + 1) * n;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  stage_row<T>(v, wb + (int64_t)J * n, n, &bar, phase);
+  for (int j = J; j >= 1; --j) {
+    stage_row<T>(wj, wb + (int64_t)(j - 1) * n, n, &bar, phase);
+    const long long stride = 1LL << (j - 1);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      T acc_h = 0, acc_g = 0;
+      for (int l = 0; l < taps.L; ++l) {
+        int idx = t + (int)((stride * l) % n);
+        if (idx >= n) idx -= n;
+        acc_h += T(taps.hi[l]) * wj[idx];
+        acc_g += T(taps.lo[l]) * v[idx];
+      }
+      vn[t] = acc_h + acc_g;
+    }
+    __syncthreads();
+    T *tmp = v; v = vn; vn = tmp;
+  }
+  for (int t = threadIdx.x; t < n; t += blockDim.x) out[b * n + t] = v[t];
+}
+
+// ---- MODWT MRA: out[b,j,t] = sum_{l<len_j} filt[j,l] w[b,j,(t+l) mod N] --------------
+template <typename T>
+__global__ void k_modwtmra(const T *__restrict__ w, int n, int J, const double *__restrict__ filt,
+                           const int *__restrict__ flen, T *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int np = (n + 3) & ~3;
+  T *row = reinterpret_cast<T *>(smem_raw);
+  T *f = row + np;
+  const int64_t b = blockIdx.x / (J + 1);
+  const int j = blockIdx.x % (J + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  const int len = flen[j];
+  for (int l = threadIdx.x; l < len; l += blockDim.x) f[l] = T(filt[(int64_t)j * n + l]);
+  stage_row<T>(row, w + (b * (J + 1) + j) * (int64_t)n, n, &bar, phase);
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    T acc = 0;
+    int idx = t;
+    for (int l = 0; l < len; ++l) {
+      acc += f[l] * row[idx];
+      if (++idx == n) idx = 0;
+    }
+    out[(b * (J + 1) + j) * (int64_t)n + t] = acc;
+  }
+}
+
+// ---- DWT (symmetric) ---------------------------------------------------------------------
+__device__ __forceinline__ int reflect_sym(int p, int n) {
+  // half-sample symmetric extension, repeated when |p| runs past one period
+  const int period = 2 * n;
+  int m = p % period;
+  if (m < 0) m += period;
+  return m >= n ? period - 1 - m : m;
+}
+
+constexpr int kMaxLevels = 32;
+struct LevelPlan {
+  int level;
+  int n;                     // signal length (wavedec) / output length (waverec)
+  int buf;                   // elements per shared-memory ping-pong buffer
+  int total;                 // packed coefficient count per series
+  int len[kMaxLevels + 1];   // cA_L, cD_L, ..., cD_1
+  int off[kMaxLevels + 1];   // offsets of those blocks in the packed row
+};
+
+// cA[i] = sum_j lo[j] xe[2i+1-j]; cD with hi.  cA stays in smem for the next level.
+template <typename T>
+__global__ void k_wavedec(const T *__restrict__ x, LevelPlan plan, Taps taps, T *__restrict__ coeffs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  T *a = reinterpret_cast<T *>(smem_raw);
+  T *an = a + plan.buf;
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  stage_row<T>(a, x + b * (int64_t)plan.n, plan.n, &bar, phase);
+  T *o = coeffs + b * (int64_t)plan.total;
+  int cur = plan.n;
+  for (int lev = 1; lev <= plan.level; ++lev) {
+    const int slot = plan.level - lev + 1;  // cD_lev
+    const int nout = plan.len[slot];
+    T *od = o + plan.off[slot];
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+      T ca = 0, cd = 0;
+      for (int j = 0; j < taps.L; ++j) {
+        const T val = a[reflect_sym(2 * i + 1 - j, cur)];
+        ca += T(taps.lo[j]) * val;
+        cd += T(taps.hi[j]) * val;
+      }
+      od[i] = cd;
+      an[i] = ca;
+    }
+    __syncthreads();
+    T *tmp = a; a = an; an = tmp;
+    cur = nout;
+  }
+  for (int i = threadIdx.x; i < cur; i += blockDim.x) o[i] = a[i];
+}
+
+// a <- idwt(a, d): full[n] = sum_k lo[n-2k] a[k] + hi[n-2k] d[k]; keep full[L-2 : L-2+2m-L+2]
+template <typename T>
+__global__ void k_waverec(const T *__restrict__ coeffs, LevelPlan plan, Taps taps, T *__restrict__ x) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *a = reinterpret_cast<T *>(smem_raw);
+  T *an = a + plan.buf;
+  const int64_t b = blockIdx.x;
+  const T *c = coeffs + b * (int64_t)plan.total;
+  int cur = plan.len[0];
+  for (int i = threadIdx.x; i < cur; i += blockDim.x) a[i] = c[i];
+  __syncthreads();
+  const int L = taps.L;
+  for (int slot = 1; slot <= plan.level; ++slot) {
+    const int m = plan.len[slot];  // == cur or cur-1 (pywt drops the extra approximation sample)
+    const T *d = c + plan.off[slot];
+    const int nout = 2 * m - L + 2;
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+      const int nn = o + L - 2;
+      int k_lo = (nn - L + 2) / 2;  // ceil((nn-L+1)/2) for nn-L+1 >= -1
+      if (nn - L + 1 < 0) k_lo = 0;
+      int k_hi = nn / 2;
+      if (k_hi > m - 1) k_hi = m - 1;
+      T acc = 0;
+      for (int k = k_lo; k <= k_hi; ++k) {
+        const int idx = nn - 2 * k;
+        acc += T(taps.lo[idx]) * a[k] + T(taps.hi[idx]) * d[k];
+      }
+      an[o] = acc;
+    }
+    __syncthreads();
+    T *tmp = a; a = an; an = tmp;
+    cur = nout;
+  }
+  for (int i = threadIdx.x; i < cur; i += blockDim.x) x[b * (int64_t)plan.n + i] = a[i];
+}
+
+// ---- host side -----------------------------------------------------------------------------
+static int make_taps(const double *lo, const double *hi, int L, double scale, Taps *t) {
+  WTB_REQUIRE(lo && hi && L >= 2 && L <= kMaxTaps, WTB_EUNSUPPORTED, "filter length %d outside [2,%d]", L, kMaxTaps);
+  t->L = L;
+  for (int i = 0; i < L; ++i) {
+    t->lo[i] = lo[i] * scale;
+    t->hi[i] = hi[i] * scale;
+  }
+  return WTB_OK;
+}
+
+// Runs `launch(d_in, d_out, rows)` over the batch, staging host buffers through the arena.
+template <typename F>
+static int run_batched(const void *in, void *out, int64_t batch, size_t in_row, size_t out_row,
+                       int flags, cudaStream_t st, F launch) {
+  if (flags & WTB_DEVICE_PTRS) return launch(in, out, batch);
+  const size_t budget = size_t(1) << 30;
+  const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(budget / (in_row + out_row))));
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  void *stage = nullptr;
+  WTB_TRY(staging_reserve(al(in_row * rows) + al(out_row * rows), &stage));
+  char *d_in = (char *)stage, *d_out = d_in + al(in_row * rows);
+  for (int64_t b0 = 0; b0 < batch; b0 += rows) {
+    const int64_t nb = std::min(rows, batch - b0);
+    WTB_CUDA(cudaMemcpyAsync(d_in, (const char *)in + b0 * in_row, in_row * nb, cudaMemcpyHostToDevice, st));
+    WTB_TRY(launch(d_in, d_out, nb));
+    WTB_CUDA(cudaMemcpyAsync((char *)out + b0 * out_row, d_out, out_row * nb, cudaMemcpyDeviceToHost, st));
+    WTB_CUDA(cudaStreamSynchronize(st));
+  }
+  return WTB_OK;
+}
+
+template <typename K> static int set_smem(K kernel, size_t bytes) {
+  WTB_REQUIRE(bytes <= 227 * 1024, WTB_EUNSUPPORTED,
+              "series too long for the in-shared-memory filterbank (%zu B > 227 KB per CTA)", bytes);
+  WTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return WTB_OK;
+}
+
+static int threads_for(int n) { return n >= 2048 ? 512 : (n >= 512 ? 256 : 128); }
+
+template <typename T>
+static int modwt_impl(const void *x, int64_t batch, int n, const Taps &taps, int J, int flags, void *out,
+                      cudaStream_t st) {
+  const size_t smem = sizeof(T) * 2 * (size_t)((n + 3) & ~3);
+  WTB_TRY(set_smem(k_modwt<T>, smem));
+  return run_batched(x, out, batch, sizeof(T) * n, sizeof(T) * (size_t)(J + 1) * n, flags, st,
+                     [&](const void *di, void *dout, int64_t nb) -> int {
+                       k_modwt<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
+                       WTB_CUDA(cudaGetLastError());
+                       return WTB_OK;
+                     });
+}
+
+template <typename T>
+static int imodwt_impl(const void *w, int64_t batch, int n, const Taps &taps, int J, int flags, void *out,
+                       cudaStream_t st) {
+  const size_t smem = sizeof(T) * 3 * (size_t)((n + 3) & ~3);
+  WTB_TRY(set_smem(k_imodwt<T>, smem));
+  return run_batched(w, out, batch, sizeof(T) * (size_t)(J + 1) * n, sizeof(T) * n, flags, st,
+                     [&](const void *di, void *dout, int64_t nb) -> int {
+                       k_imodwt<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
+                       WTB_CUDA(cudaGetLastError());
+                       return WTB_OK;
+                     });
+}
+
+template <typename T>
+static int mra_impl(const void *w, int64_t batch, int n, const double *filt, int J, int flags, void *out,
+                    cudaStream_t st) {
+  const size_t smem = sizeof(T) * 2 * (size_t)((n + 3) & ~3);
+  WTB_TRY(set_smem(k_modwtmra<T>, smem));
+  // effective filter length per level (trailing zeros of the periodised filter are skipped)
+  std::vector<int> flen(J + 1);
+  for (int j = 0; j <= J; ++j) {
+    int len = n;
+    while (len > 0 && filt[(size_t)j * n + len - 1] == 0.0) --len;
+    flen[j] = len;
+  }
+  void *scratch = nullptr;
+  const size_t b_f = (sizeof(double) * (size_t)(J + 1) * n + 255) / 256 * 256;
+  WTB_TRY(arena_reserve(b_f + sizeof(int) * (J + 1), &scratch));
+  double *d_filt = (double *)scratch;
+  int *d_flen = (int *)((char *)scratch + b_f);
+  WTB_CUDA(cudaMemcpyAsync(d_filt, filt, sizeof(double) * (size_t)(J + 1) * n, cudaMemcpyHostToDevice, st));
+  WTB_CUDA(cudaMemcpyAsync(d_flen, flen.data(), sizeof(int) * (J + 1), cudaMemcpyHostToDevice, st));
+  WTB_CUDA(cudaStreamSynchronize(st));  // flen is a local
+  const size_t row = sizeof(T) * (size_t)(J + 1) * n;
+  return run_batched(w, out, batch, row, row, flags, st, [&](const void *di, void *dout, int64_t nb) -> int {
+    WTB_REQUIRE(nb * (J + 1) < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+    k_modwtmra<T><<<(unsigned)(nb * (J + 1)), threads_for(n), smem, st>>>((const T *)di, n, J, d_filt, d_flen, (T *)dout);
+    WTB_CUDA(cudaGetLastError());
+    return WTB_OK;
+  });
+}
+
+static int make_plan(int n, int L, int level, const int *lens_in, LevelPlan *p) {
+  WTB_REQUIRE(level >= 0 && level <= kMaxLevels, WTB_EUNSUPPORTED, "level %d outside [0,%d]", level, kMaxLevels);
+  p->level = level;
+  p->n = n;
+  if (lens_in) {
+    for (int i = 0; i <= level; ++i) p->len[i] = lens_in[i];
+  } else {
+    WTB_TRY(wtb_dwt_coeff_lens(n, L, level, p->len));
+  }
+  int off = 0;
+  for (int i = 0; i <= level; ++i) {
+    WTB_REQUIRE(p->len[i] > 0, WTB_EINVAL, "empty coefficient block %d", i);
+    p->off[i] = off;
+    off += p->len[i];
+  }
+  p->total = off;
+  return WTB_OK;
+}
+
+template <typename T>
+static int wavedec_impl(const void *x, int64_t batch, int n, const Taps &taps, int level, int flags,
+                        void *coeffs, cudaStream_t st) {
+  LevelPlan plan;
+  WTB_TRY(make_plan(n, taps.L, level, nullptr, &plan));
+  plan.buf = (n + 3) & ~3;
+  const size_t smem = sizeof(T) * 2 * (size_t)plan.buf;
+  WTB_TRY(set_smem(k_wavedec<T>, smem));
+  return run_batched(x, coeffs, batch, sizeof(T) * n, sizeof(T) * (size_t)plan.total, flags, st,
+                     [&](const void *di, void *dout, int64_t nb) -> int {
+                       k_wavedec<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, plan, taps, (T *)dout);
+                       WTB_CUDA(cudaGetLastError());
+                       return WTB_OK;
+                     });
+}
+
+template <typename T>
+static int waverec_impl(const void *coeffs, int64_t batch, const int *lens, int level, const Taps &taps,
+                        int flags, void *x, cudaStream_t st) {
+  const int nout = wtb_waverec_len(lens, level, taps.L);
+  if (nout < 0) return nout;
+  LevelPlan plan;
+  WTB_TRY(make_plan(nout, taps.L, level, lens, &plan));
+  int longest = nout;
+  for (int i = 0; i <= level; ++i) longest = std::max(longest, plan.len[i]);
+  plan.buf = (longest + taps.L + 3) & ~3;
+  const size_t smem = sizeof(T) * 2 * (size_t)plan.buf;
+  WTB_TRY(set_smem(k_waverec<T>, smem));
+  return run_batched(coeffs, x, batch, sizeof(T) * (size_t)plan.total, sizeof(T) * (size_t)nout, flags, st,
+                     [&](const void *di, void *dout, int64_t nb) -> int {
+                       k_waverec<T><<<(unsigned)nb, threads_for(nout), smem, st>>>((const T *)di, plan, taps, (T *)dout);
+                       WTB_CUDA(cudaGetLastError());
+                       return WTB_OK;
+                     });
+}
+
+}  // namespace wtb
+
+using namespace wtb;
+
+#define DISPATCH(fn, ...) ((flags & WTB_F64) ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+extern "C" int wtb_modwt(const void *x, int64_t batch, int n, const double *g, const double *h, int L,
+                         int J, int flags, void *w_out, void *stream) {
+  WTB_REQUIRE(x && w_out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_modwt: bad arguments");
+  Taps taps;
+  WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  return DISPATCH(modwt_impl, x, batch, n, taps, J, flags, w_out, (cudaStream_t)stream);
+}
+
+extern "C" int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, const double *h, int L,
+                          int J, int flags, void *x_out, void *stream) {
+  WTB_REQUIRE(w && x_out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_imodwt: bad arguments");
+  Taps taps;
+  WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  return DISPATCH(imodwt_impl, w, batch, n, taps, J, flags, x_out, (cudaStream_t)stream);
+}
+
+extern "C" int wtb_modwtmra(const void *w, int64_t batch, int n, const double *filt, int J, int flags,
+                            void *out, void *stream) {
+  WTB_REQUIRE(w && out && filt && batch >= 0 && n > 0 && J >= 1, WTB_EINVAL, "wtb_modwtmra: bad arguments");
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  return DISPATCH(mra_impl, w, batch, n, filt, J, flags, out, (cudaStream_t)stream);
+}
+
+extern "C" int wtb_wavedec(const void *x, int64_t batch, int n, const double *dec_lo, const double *dec_hi,
+                           int L, int level, int flags, void *coeffs, void *stream) {
+  WTB_REQUIRE(x && coeffs && batch >= 0 && n > 0 && level >= 0, WTB_EINVAL, "wtb_wavedec: bad arguments");
+  Taps taps;
+  WTB_TRY(make_taps(dec_lo, dec_hi, L, 1.0, &taps));
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  return DISPATCH(wavedec_impl, x, batch, n, taps, level, flags, coeffs, (cudaStream_t)stream);
+}
+
+extern "C" int wtb_waverec(const void *coeffs, int64_t batch, const int *lens, int level, const double *rec_lo,
+                           const double *rec_hi, int L, int flags, void *x_out, void *stream) {
+  WTB_REQUIRE(coeffs && x_out && lens && batch >= 0 && level >= 0, WTB_EINVAL, "wtb_waverec: bad arguments");
+  Taps taps;
+  WTB_TRY(make_taps(rec_lo, rec_hi, L, 1.0, &taps));
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  return DISPATCH(waverec_impl, coeffs, batch, lens, level, taps, flags, x_out, (cudaStream_t)stream);
+}

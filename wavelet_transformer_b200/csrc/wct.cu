@@ -1,0 +1,378 @@
+// Cross-wavelet / wavelet-coherence pipeline (pycwt.xwt, pycwt.wct,
+// pycwt.wct_significance; reference call sites src/wct.py:106, src/xwt.py:93,122).
+//
+//   k_fwd_fft            X1, X2 = fft(y1), fft(y2)                     (cwt.cu)
+//   k_wct_rows  (b, s)   W1, W2 = ifft(X * daughter_s)
+//                        P  = (|W1|^2 + i |W2|^2) / s       two real fields packed in one FFT
+//                        C  = W1 conj(W2) / s
+//                        T  = ifft(gauss_s * fft(.))        time smoothing (Morlet.smooth)
+//                        -> tsm[b, s, t] = (T1, T2, Re T12, Im T12)
+//   k_wct_scale (b, t)   boxcar over scales (convolve2d 'same', zero fill), then
+//                        WCT = |S12|^2 / (S1 S2)  -> output plane, or -> histogram bins
+//
+// The Gaussian filter is real and even, so filtering the packed field P gives
+// smooth(|W1|^2) in its real part and smooth(|W2|^2) in its imaginary part.
+#include "spectral.cuh"
+
+namespace wtb {
+
+template <typename T> struct vec4_of;
+template <> struct vec4_of<float> { using type = float4; };
+template <> struct vec4_of<double> { using type = double4; };
+template <typename T> using vec4 = typename vec4_of<T>::type;
+
+// One CTA = one (pair, scale).  smem: 3 * N complex (U, V, tmp).
+// xhat: [pairs, 2, N].  tsm: [pairs, S, n0] vec4.  phase/w12 optional [pairs,S,n0].
+template <typename T>
+__global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
+                           const double *__restrict__ scales, double dt, double f0,
+                           const cplx<T> *__restrict__ tw, vec4<T> *__restrict__ tsm,
+                           T *__restrict__ phase, cplx<T> *__restrict__ w12, int smooth) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<T> *U = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *V = U + N;
+  cplx<T> *Tm = V + N;
+  const int64_t pair = blockIdx.x / S;
+  const int s = blockIdx.x % S;
+  const cplx<T> *x1 = xhat + (pair * 2) * (int64_t)N;
+  const cplx<T> *x2 = x1 + N;
+  const double sc = scales[s];
+  const T s_over_dt = T(sc / dt);
+  const T norm = T(sqrt(2.0 * kPi * sc / dt) * kPiM14 / double(N));
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const T d = morlet_daughter<T>(k, N, s_over_dt, norm, T(f0));
+    const cplx<T> a = x1[k], b = x2[k];
+    U[k] = mk<T>(a.x * d, a.y * d);
+    V[k] = mk<T>(b.x * d, b.y * d);
+  }
+  __syncthreads();
+  cplx<T> *r;
+  r = block_fft<T, +1>(U, Tm, N, log2N, tw);
+  if (r != U) { Tm = U; U = r; }
+  r = block_fft<T, +1>(V, Tm, N, log2N, tw);
+  if (r != V) { Tm = V; V = r; }
+  // U = W1 row, V = W2 row (valid for t < n0; pycwt truncates before smoothing)
+  const int64_t obase = (pair * S + s) * (int64_t)n0;
+  const T inv_s = T(1.0 / sc);
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    cplx<T> p = mk<T>(T(0), T(0)), c = p;
+    if (t < n0) {
+      const cplx<T> a = U[t], b = V[t];
+      const cplx<T> x = cmulc(a, b);  // W1 * conj(W2)
+      if (w12) w12[obase + t] = x;
+      if (phase) phase[obase + t] = dev_atan2<T>(x.y, x.x);
+      p = mk<T>((a.x * a.x + a.y * a.y) * inv_s, (b.x * b.x + b.y * b.y) * inv_s);
+      c = mk<T>(x.x * inv_s, x.y * inv_s);
+    }
+    U[t] = p;
+    V[t] = c;
+  }
+  if (!smooth) return;
+  __syncthreads();
+  r = block_fft<T, -1>(U, Tm, N, log2N, tw);
+  if (r != U) { Tm = U; U = r; }
+  r = block_fft<T, -1>(V, Tm, N, log2N, tw);
+  if (r != V) { Tm = V; V = r; }
+  // Gaussian in the Fourier domain: exp(-0.5 (s/dt)^2 k^2), k = 2*pi*fftfreq(N)
+  const T invN = T(1.0 / N);
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const int kk = (k < (N + 1) / 2) ? k : k - N;
+    const T w = T(2.0 * kPi) * T(kk) / T(N) * s_over_dt;
+    const T g = dev_exp<T>(T(-0.5) * w * w) * invN;
+    cplx<T> p = U[k], c = V[k];
+    U[k] = mk<T>(p.x * g, p.y * g);
+    V[k] = mk<T>(c.x * g, c.y * g);
+  }
+  __syncthreads();
+  r = block_fft<T, +1>(U, Tm, N, log2N, tw);
+  if (r != U) { Tm = U; U = r; }
+  r = block_fft<T, +1>(V, Tm, N, log2N, tw);
+  if (r != V) { Tm = V; V = r; }
+  for (int t = threadIdx.x; t < n0; t += blockDim.x) {
+    const cplx<T> p = U[t], c = V[t];
+    vec4<T> o;
+    o.x = p.x; o.y = p.y; o.z = c.x; o.w = c.y;
+    tsm[obase + t] = o;
+  }
+}
+
+constexpr int kMaxWin = 64;
+struct ScaleWin {
+  int K;          // taps
+  int up;         // (K-1)/2: out[i] = sum_k win[k] * T[i + up - k]
+  double w[kMaxWin];
+};
+
+// One thread = one (pair, t) column; walks the scales.  MODE 0: write WCT plane;
+// MODE 1: add to the per-scale histogram for t inside [tlo[s], thi[s]] and s < maxscale.
+template <typename T, int MODE>
+__global__ void k_wct_scale(const vec4<T> *__restrict__ tsm, int64_t pairs, int n0, int S,
+                            ScaleWin win, T *__restrict__ wct,
+                            unsigned long long *__restrict__ hist, const int *__restrict__ tlo,
+                            const int *__restrict__ thi, int maxscale) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= pairs * n0) return;
+  const int64_t pair = gid / n0;
+  const int t = (int)(gid % n0);
+  const vec4<T> *col = tsm + pair * (int64_t)S * n0 + t;
+  const int s_end = MODE == 1 ? maxscale : S;
+  for (int s = 0; s < s_end; ++s) {
+    if (MODE == 1 && (t < tlo[s] || t > thi[s])) continue;
+    T s1 = 0, s2 = 0, cr = 0, ci = 0;
+    for (int k = 0; k < win.K; ++k) {
+      const int row = s + win.up - k;
+      if (row < 0 || row >= S) continue;
+      const vec4<T> v = col[(int64_t)row * n0];
+      const T w = T(win.w[k]);
+      s1 += w * v.x; s2 += w * v.y; cr += w * v.z; ci += w * v.w;
+    }
+    const T r2 = (cr * cr + ci * ci) / (s1 * s2);
+    if (MODE == 0) {
+      wct[(pair * S + s) * (int64_t)n0 + t] = r2;
+    } else {
+      if (r2 >= T(0)) {  // NaN (0/0) is skipped
+        int bin = (int)floor(r2 * T(WTB_NBINS));
+        bin = min(bin, WTB_NBINS - 1);
+        atomicAdd(&hist[(size_t)s * WTB_NBINS + bin], 1ULL);
+      }
+    }
+  }
+}
+
+static int make_win(double dj, ScaleWin *win) {
+  // Morlet.smooth: rect(int(round(deltaj0/dj*2)), normalize=True), deltaj0 = 0.6
+  const int K = (int)std::nearbyint(0.6 / dj * 2);
+  WTB_REQUIRE(K >= 1 && K <= kMaxWin, WTB_EUNSUPPORTED, "scale window of %d taps (dj=%g) unsupported", K, dj);
+  win->K = K;
+  win->up = (K - 1) / 2;
+  double sum = 0;
+  for (int k = 0; k < K; ++k) {
+    win->w[k] = (k == 0 || k == K - 1) ? 0.5 : 1.0;
+    sum += win->w[k];
+  }
+  for (int k = 0; k < K; ++k) win->w[k] /= sum;
+  return WTB_OK;
+}
+
+// Shared device pipeline.  d_y: [pairs, 2, n0] (series interleaved per pair).
+template <typename T>
+static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, double dj,
+                      const Axes &ax, double f0, T *d_wct, T *d_phase, cplx<T> *d_w12,
+                      unsigned long long *d_hist, const int *h_tlo, const int *h_thi, int maxscale,
+                      cudaStream_t st) {
+  const int S = ax.J + 1;
+  const bool smooth = d_wct || d_hist;
+  const size_t smem_fwd = 2 * sizeof(cplx<T>) * (size_t)N;
+  const size_t smem_rows = 3 * sizeof(cplx<T>) * (size_t)N;
+  WTB_REQUIRE(smem_rows <= 227 * 1024, WTB_EUNSUPPORTED,
+              "nfft=%d needs %zu B of shared memory per CTA (limit 227 KB): max nfft is %d for %s",
+              N, smem_rows, sizeof(T) == 4 ? 8192 : 4096, sizeof(T) == 4 ? "float" : "double");
+  ScaleWin win;
+  WTB_TRY(make_win(dj, &win));
+  const cplx<T> *tw = nullptr;
+  WTB_TRY(twiddles<T>(N, &tw));
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_sc = al(sizeof(double) * S);
+  const size_t b_rng = al(sizeof(int) * S);
+  const size_t b_xh = al(sizeof(cplx<T>) * (size_t)pairs * 2 * N);
+  const size_t b_ts = smooth ? al(sizeof(vec4<T>) * (size_t)pairs * S * n0) : 0;
+  void *scratch = nullptr;
+  WTB_TRY(arena_reserve(b_sc + 2 * b_rng + b_xh + b_ts, &scratch));
+  char *p = (char *)scratch;
+  double *d_scales = (double *)p; p += b_sc;
+  int *d_tlo = (int *)p; p += b_rng;
+  int *d_thi = (int *)p; p += b_rng;
+  cplx<T> *d_xhat = (cplx<T> *)p; p += b_xh;
+  vec4<T> *d_tsm = (vec4<T> *)p;
+  WTB_CUDA(cudaMemcpyAsync(d_scales, ax.scales.data(), sizeof(double) * S, cudaMemcpyHostToDevice, st));
+  if (d_hist) {
+    WTB_CUDA(cudaMemcpyAsync(d_tlo, h_tlo, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    WTB_CUDA(cudaMemcpyAsync(d_thi, h_thi, sizeof(int) * S, cudaMemcpyHostToDevice, st));
+  }
+  const int log2N = ilog2(N);
+  const int threads = N >= 1024 ? 256 : (N >= 256 ? 128 : 64);
+  WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
+  WTB_CUDA(cudaFuncSetAttribute(k_wct_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+  WTB_REQUIRE(pairs * S < (1LL << 31) && pairs * 2 < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+  k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
+  WTB_CUDA(cudaGetLastError());
+  k_wct_rows<T><<<(unsigned)(pairs * S), threads, smem_rows, st>>>(
+      d_xhat, n0, N, log2N, S, d_scales, dt, f0, tw, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
+  WTB_CUDA(cudaGetLastError());
+  if (smooth) {
+    const int64_t cols = pairs * n0;
+    const unsigned blocks = (unsigned)((cols + 255) / 256);
+    if (d_hist)
+      k_wct_scale<T, 1><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, nullptr, d_hist, d_tlo, d_thi, maxscale);
+    else
+      k_wct_scale<T, 0><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, d_wct, nullptr, nullptr, nullptr, 0);
+    WTB_CUDA(cudaGetLastError());
+  }
+  return WTB_OK;
+}
+
+// bytes of arena + staging one pair costs (for batching decisions)
+template <typename T> static size_t pair_bytes(int n0, int N, int S) {
+  return sizeof(cplx<T>) * 2 * (size_t)N + sizeof(vec4<T>) * (size_t)S * n0;
+}
+
+template <typename T>
+static int xwt_wct_entry(const void *y1, const void *y2, int64_t batch, int n0, int N, double dt,
+                         double dj, const Axes &ax, double f0, int flags, void *wct_out,
+                         void *phase_out, void *w12_out, cudaStream_t st) {
+  const int S = ax.J + 1;
+  const size_t plane = (size_t)S * n0;
+  // stage inputs interleaved [pair, 2, n0] and outputs per chunk
+  const size_t per_pair = sizeof(T) * (2 * (size_t)n0 + (wct_out ? plane : 0) + (phase_out ? plane : 0) +
+                                       (w12_out ? 2 * plane : 0));
+  const size_t budget = size_t(1) << 30;
+  const int64_t rows = std::max<int64_t>(
+      1, std::min<int64_t>(batch, (int64_t)(budget / (per_pair + pair_bytes<T>(n0, N, S)))));
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  void *stage = nullptr;
+  WTB_TRY(staging_reserve(al(sizeof(T) * rows * 2 * n0) + al(sizeof(T) * rows * plane) * 4 + 1024, &stage));
+  char *p = (char *)stage;
+  T *d_y = (T *)p; p += al(sizeof(T) * rows * 2 * n0);
+  T *d_wct = nullptr, *d_phase = nullptr;
+  cplx<T> *d_w12 = nullptr;
+  const bool dev = flags & WTB_DEVICE_PTRS;
+  if (wct_out) { d_wct = (T *)p; p += al(sizeof(T) * rows * plane); }
+  if (phase_out) { d_phase = (T *)p; p += al(sizeof(T) * rows * plane); }
+  if (w12_out) { d_w12 = (cplx<T> *)p; }
+  const cudaMemcpyKind in_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  for (int64_t b0 = 0; b0 < batch; b0 += rows) {
+    const int64_t nb = std::min(rows, batch - b0);
+    // interleave y1/y2 rows: dst pitch 2*n0, src pitch n0
+    WTB_CUDA(cudaMemcpy2DAsync(d_y, sizeof(T) * 2 * n0, (const T *)y1 + b0 * n0, sizeof(T) * n0,
+                               sizeof(T) * n0, nb, in_kind, st));
+    WTB_CUDA(cudaMemcpy2DAsync(d_y + n0, sizeof(T) * 2 * n0, (const T *)y2 + b0 * n0, sizeof(T) * n0,
+                               sizeof(T) * n0, nb, in_kind, st));
+    T *o_wct = dev && wct_out ? (T *)wct_out + b0 * plane : d_wct;
+    T *o_phase = dev && phase_out ? (T *)phase_out + b0 * plane : d_phase;
+    cplx<T> *o_w12 = dev && w12_out ? (cplx<T> *)w12_out + b0 * plane : d_w12;
+    WTB_TRY(wct_device<T>(d_y, nb, n0, N, dt, dj, ax, f0, o_wct, o_phase, o_w12, nullptr, nullptr,
+                          nullptr, 0, st));
+    if (!dev) {
+      if (wct_out)
+        WTB_CUDA(cudaMemcpyAsync((T *)wct_out + b0 * plane, d_wct, sizeof(T) * nb * plane, out_kind, st));
+      if (phase_out)
+        WTB_CUDA(cudaMemcpyAsync((T *)phase_out + b0 * plane, d_phase, sizeof(T) * nb * plane, out_kind, st));
+      if (w12_out)
+        WTB_CUDA(cudaMemcpyAsync((cplx<T> *)w12_out + b0 * plane, d_w12, sizeof(cplx<T>) * nb * plane, out_kind, st));
+      WTB_CUDA(cudaStreamSynchronize(st));
+    } else if (b0 + rows < batch) {
+      WTB_CUDA(cudaStreamSynchronize(st));  // arena reuse across chunks
+    }
+  }
+  return WTB_OK;
+}
+
+// implemented in noise.cu
+template <typename T>
+int rednoise_device(double a1, double a2, int nsurr, int64_t first, int64_t count, uint64_t seed,
+                    bool white, T *d_out, cudaStream_t st);
+
+// Reliable-region column range per scale, evaluated in double exactly as pycwt does.
+static void coi_ranges(int nsurr, double dt, const Axes &ax, double f0, std::vector<int> *tlo,
+                       std::vector<int> *thi, std::vector<uint8_t> *any) {
+  const int S = ax.J + 1;
+  const double c = morlet_flambda(f0) / std::sqrt(2.0) * dt;
+  tlo->assign(S, 1);
+  thi->assign(S, 0);
+  any->assign(S, 0);
+  for (int s = 0; s < S; ++s) {
+    const double period = 1.0 / ax.freqs[s];
+    int lo = -1, hi = -2;
+    for (int t = 0; t < nsurr; ++t) {
+      const double coi = c * (nsurr / 2.0 - std::fabs(t - (nsurr - 1) / 2.0));
+      if (period <= coi) { if (lo < 0) lo = t; hi = t; }
+    }
+    if (lo >= 0) { (*tlo)[s] = lo; (*thi)[s] = hi; (*any)[s] = 1; }
+  }
+}
+
+template <typename T>
+static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes &ax, double f0,
+                         int nsurr, int maxscale, int64_t mc_first, int64_t mc_count, uint64_t seed,
+                         const void *surrogates, int flags, uint64_t *hist, cudaStream_t st) {
+  const int S = ax.J + 1;
+  const int N = 1 << ilog2(nsurr);
+  std::vector<int> tlo, thi;
+  std::vector<uint8_t> any;
+  coi_ranges(nsurr, dt, ax, f0, &tlo, &thi, &any);
+  const bool dev = flags & WTB_DEVICE_PTRS;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t per_pair = sizeof(T) * 2 * (size_t)nsurr + pair_bytes<T>(nsurr, N, S);
+  const size_t budget = size_t(3) << 29;  // 1.5 GiB of intermediates per chunk
+  const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(mc_count, (int64_t)(budget / per_pair)));
+  void *stage = nullptr;
+  const size_t b_hist = al(sizeof(uint64_t) * S * WTB_NBINS);
+  WTB_TRY(staging_reserve(al(sizeof(T) * rows * 2 * nsurr) + b_hist, &stage));
+  T *d_y = (T *)stage;
+  unsigned long long *d_hist = (unsigned long long *)((char *)stage + al(sizeof(T) * rows * 2 * nsurr));
+  unsigned long long *hist_dev = dev ? (unsigned long long *)hist : d_hist;
+  if (!dev) WTB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * S * WTB_NBINS, st));
+  for (int64_t m0 = 0; m0 < mc_count; m0 += rows) {
+    const int64_t nb = std::min(rows, mc_count - m0);
+    const T *src = d_y;
+    if (surrogates) {
+      const T *sp = (const T *)surrogates + m0 * 2 * nsurr;
+      if (dev) src = sp;
+      else WTB_CUDA(cudaMemcpyAsync(d_y, sp, sizeof(T) * nb * 2 * nsurr, cudaMemcpyHostToDevice, st));
+    } else {
+      WTB_TRY(rednoise_device<T>(a1, a2, nsurr, mc_first + m0, nb, seed, flags & WTB_NOISE_WHITE, d_y, st));
+    }
+    WTB_TRY(wct_device<T>(src, nb, nsurr, N, dt, dj, ax, f0, nullptr, nullptr, nullptr, hist_dev,
+                          tlo.data(), thi.data(), maxscale, st));
+    if (m0 + rows < mc_count) WTB_CUDA(cudaStreamSynchronize(st));  // arena reuse across chunks
+  }
+  if (!dev) {
+    std::vector<uint64_t> h((size_t)S * WTB_NBINS);
+    WTB_CUDA(cudaMemcpyAsync(h.data(), d_hist, sizeof(uint64_t) * h.size(), cudaMemcpyDeviceToHost, st));
+    WTB_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < h.size(); ++i) hist[i] += h[i];
+  }
+  return WTB_OK;
+}
+
+}  // namespace wtb
+
+using namespace wtb;
+
+extern "C" int wtb_xwt_wct(const void *y1, const void *y2, int64_t batch, int n0, int nfft, double dt,
+                           double dj, double s0, int J, double f0, int flags, void *wct_out,
+                           void *phase_out, void *w12_out, void *stream) {
+  WTB_REQUIRE(y1 && y2 && batch >= 0 && n0 > 0, WTB_EINVAL, "wtb_xwt_wct: bad inputs");
+  WTB_REQUIRE(wct_out || phase_out || w12_out, WTB_EINVAL, "wtb_xwt_wct: no output requested");
+  WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
+              "nfft=%d must be a power of two >= n0=%d", nfft, n0);
+  WTB_TRY(ensure_device());
+  Axes ax;
+  WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));
+  if (batch == 0) return WTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & WTB_F64)
+    return xwt_wct_entry<double>(y1, y2, batch, n0, nfft, dt, dj, ax, f0, flags, wct_out, phase_out, w12_out, st);
+  return xwt_wct_entry<float>(y1, y2, batch, n0, nfft, dt, dj, ax, f0, flags, wct_out, phase_out, w12_out, st);
+}
+
+extern "C" int wtb_wct_mc_hist(double a1, double a2, double dt, double dj, double s0, int J, double f0,
+                               int64_t mc_first, int64_t mc_count, uint64_t seed, const void *surrogates,
+                               int flags, uint64_t *hist, void *stream) {
+  WTB_REQUIRE(hist && mc_count >= 0 && mc_first >= 0, WTB_EINVAL, "wtb_wct_mc_hist: bad arguments");
+  WTB_REQUIRE(J >= 0, WTB_EINVAL, "wtb_wct_mc_hist needs a resolved J");
+  WTB_REQUIRE(fabs(a1) < 1 && fabs(a2) < 1, WTB_EINVAL, "AR(1) coefficients must lie in (-1, 1)");
+  WTB_TRY(ensure_device());
+  int nsurr = 0, maxscale = 0;
+  WTB_TRY(wtb_wct_mc_geometry(dt, dj, s0, J, f0, &nsurr, &maxscale));
+  Axes ax;
+  WTB_TRY(resolve_axes(nsurr, dt, dj, s0, J, f0, &ax));
+  if (mc_count == 0) return WTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & WTB_F64)
+    return mc_hist_entry<double>(a1, a2, dt, dj, ax, f0, nsurr, maxscale, mc_first, mc_count, seed,
+                                 surrogates, flags, hist, st);
+  return mc_hist_entry<float>(a1, a2, dt, dj, ax, f0, nsurr, maxscale, mc_first, mc_count, seed,
+                              surrogates, flags, hist, st);
+}

@@ -1,0 +1,311 @@
+"""pycwt-shaped facade over the B200 engine.
+
+The reference reaches its CWT/XWT/WCT numerics through ``import pycwt as
+wavelet`` (src/cwt.py:19, src/wct.py:14, src/xwt.py:12,
+constants/results_configs.py:4).  Swapping that line for
+``from wavelet_transformer_b200 import pycwt_compat as wavelet`` keeps every
+call site unchanged: same function names, argument order, return tuples, and
+the ``Warning`` that ``ar1`` raises for an unbounded AR(1) estimate (caught at
+src/wavelet_plots.py:684).
+
+Heavy arithmetic (transforms, smoothing, Monte Carlo) runs in
+libwavelet_sm100a.so; only O(n) closed forms (``ar1``, ``significance``, axes)
+stay on the host.  Outputs are float64 / complex128 like pycwt's.
+"""
+
+from __future__ import annotations
+
+import math
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import _shim
+
+__all__ = ["Morlet", "Paul", "DOG", "MexicanHat", "ar1", "ar1_spectrum", "significance", "cwt", "xwt",
+           "wct", "wct_significance", "rednoise", "rect"]
+
+
+class Morlet:
+    """Morlet mother wavelet, pycwt.mothers.Morlet attribute-compatible."""
+
+    name = "morlet"
+
+    def __init__(self, f0: float = 6):
+        self.f0 = f0
+        self.dofmin = 2
+        if f0 == 6:
+            self.cdelta, self.gamma, self.deltaj0 = 0.776, 2.32, 0.60
+        else:
+            self.cdelta = self.gamma = self.deltaj0 = -1
+
+    def psi_ft(self, f):
+        return np.pi ** -0.25 * np.exp(-0.5 * (np.asarray(f) - self.f0) ** 2)
+
+    def psi(self, t):
+        t = np.asarray(t)
+        return np.pi ** -0.25 * np.exp(1j * self.f0 * t - t ** 2 / 2)
+
+    def flambda(self):
+        return 4 * np.pi / (self.f0 + np.sqrt(2 + self.f0 ** 2))
+
+    def coi(self):
+        return 1.0 / np.sqrt(2)
+
+    def sup(self):
+        return 1.0 / self.coi()
+
+
+class _StubMother:
+    """Paul / DOG are constructed at import time by the reference
+    (src/wct.py:36-41, constants/results_configs.py:53-58) but never selected
+    (XWT_MOTHER = "morlet"); the engine only transforms with Morlet."""
+
+    name = "stub"
+
+    def _unsupported(self, *_a, **_k):
+        raise NotImplementedError(
+            f"{type(self).__name__}: only the Morlet wavelet is implemented on the B200 engine")
+
+    psi_ft = psi = smooth = _unsupported
+
+
+class Paul(_StubMother):
+    name = "paul"
+
+    def __init__(self, m: int = 4):
+        self.m = m
+        self.dofmin = 2
+        if m == 4:
+            self.cdelta, self.gamma, self.deltaj0 = 1.132, 1.17, 1.50
+        else:
+            self.cdelta = self.gamma = self.deltaj0 = -1
+
+    def flambda(self):
+        return 4 * np.pi / (2 * self.m + 1)
+
+    def coi(self):
+        return np.sqrt(2)
+
+
+class DOG(_StubMother):
+    name = "dog"
+
+    def __init__(self, m: int = 2):
+        self.m = m
+        self.dofmin = 1
+        if m == 2:
+            self.cdelta, self.gamma, self.deltaj0 = 3.541, 1.43, 1.40
+        elif m == 6:
+            self.cdelta, self.gamma, self.deltaj0 = 1.966, 1.37, 0.97
+        else:
+            self.cdelta = self.gamma = self.deltaj0 = -1
+
+    def flambda(self):
+        return 2 * np.pi / np.sqrt(self.m + 0.5)
+
+    def coi(self):
+        return 1.0 / np.sqrt(2)
+
+
+class MexicanHat(DOG):
+    name = "mexicanhat"
+
+    def __init__(self):
+        super().__init__(m=2)
+
+
+def _as_morlet(wavelet) -> Morlet:
+    if isinstance(wavelet, str):
+        if wavelet.lower() == "morlet":
+            return Morlet(6)
+        raise NotImplementedError(f"wavelet '{wavelet}': only Morlet is implemented on the B200 engine")
+    if isinstance(wavelet, Morlet) or getattr(wavelet, "name", None) == "morlet":
+        return wavelet
+    raise NotImplementedError("only the Morlet wavelet is implemented on the B200 engine")
+
+
+def rect(n, normalize=False):
+    w = np.ones(int(n))
+    w[0] = w[-1] = 0.5
+    return w / w.sum() if normalize else w
+
+
+def ar1(x):
+    """Allen & Smith (1996) lag-1 autocorrelation.  Raises ``Warning`` (an
+    Exception subclass, as pycwt does) when no upper bound can be placed."""
+    x = np.asarray(x, dtype=float)
+    N = x.size
+    d = x - x.mean()
+    c0 = float(d @ d) / N
+    c1 = float(d[:-1] @ d[1:]) / (N - 1)
+    A = c0 * N ** 2
+    B = -c1 * N - c0 * N ** 2 - 2 * c0 + 2 * c1 - c1 * N ** 2 + c0 * N
+    Cq = N * (c0 + c1 * N - c1)
+    disc = B ** 2 - 4 * A * Cq
+    if not disc > 0:
+        raise Warning("Cannot place an upperbound on the unbiased AR(1). "
+                      "Series is too short or trend is to large.")
+    g = (-B - disc ** 0.5) / (2 * A)
+    mu2 = -1 / N + (2 / N ** 2) * ((N - g ** N) / (1 - g) - g * (1 - g ** (N - 1)) / (1 - g) ** 2)
+    a = ((1 - g ** 2) * c0 / (1 - mu2)) ** 0.5
+    return g, a, mu2
+
+
+def ar1_spectrum(freqs, ar1=0.0):
+    freqs = np.asarray(freqs)
+    return (1 - ar1 ** 2) / np.abs(1 - ar1 * np.exp(-2j * np.pi * freqs)) ** 2
+
+
+def _chi2_ppf(level, dof):
+    if dof == 2:
+        return -2.0 * math.log1p(-level)
+    from scipy.stats import chi2
+    return chi2.ppf(level, dof)
+
+
+def significance(signal, dt, scales, sigma_test=0, alpha=None, significance_level=0.95, dof=-1,
+                 wavelet="morlet"):
+    """Red-noise significance levels (Torrence & Compo 1998 sec. 4); returns
+    ``(signif, fft_theor)``.  sigma_test 0 (no smoothing) and 1 (time average)."""
+    wavelet = _as_morlet(wavelet)
+    try:
+        n0 = len(signal)
+    except TypeError:
+        n0 = 1
+    scales = np.asarray(scales, dtype=float)
+    variance = signal if n0 == 1 else np.asarray(signal).std() ** 2
+    if alpha is None:
+        alpha, _, _ = ar1(signal)
+    freq = dt / (scales * wavelet.flambda())
+    fft_theor = variance * (1 - alpha ** 2) / (1 + alpha ** 2 - 2 * alpha * np.cos(2 * np.pi * freq))
+    dofmin = wavelet.dofmin
+    if sigma_test == 0:
+        signif = fft_theor * _chi2_ppf(significance_level, dofmin) / dofmin
+    elif sigma_test == 1:
+        from scipy.stats import chi2
+        dofv = np.full(scales.shape, float(dof)) if np.ndim(dof) == 0 else np.asarray(dof, dtype=float)
+        dofv = np.maximum(dofv, 1.0)
+        dofv = dofmin * np.sqrt(1 + (dofv * dt / wavelet.gamma / scales) ** 2)
+        dofv = np.maximum(dofv, dofmin)
+        signif = fft_theor * chi2.ppf(significance_level, dofv) / dofv
+    else:
+        raise NotImplementedError("significance: sigma_test must be 0 or 1")
+    return signif, fft_theor
+
+
+def _resolve_s0_J(n0, dt, dj, s0, J, wavelet):
+    Jr, scales, freqs, coi = _shim.cwt_axes(n0, dt, dj, s0, int(J) if J != -1 else -1, wavelet.f0)
+    return Jr, scales, freqs, coi
+
+
+def cwt(signal, dt, dj=1 / 12, s0=-1, J=-1, wavelet="morlet", freqs=None):
+    """Continuous wavelet transform.  Returns ``(W, sj, freqs, coi, fft, fftfreqs)``
+    with ``W`` complex128 of shape [J+1, n0]."""
+    wavelet = _as_morlet(wavelet)
+    if freqs is not None:
+        raise NotImplementedError("custom `freqs` are not supported; use dj/s0/J")
+    x = np.ascontiguousarray(signal, dtype=float)
+    n0 = x.size
+    Jr, sj, fr, coi = _resolve_s0_J(n0, dt, dj, s0, J, wavelet)
+    _, W = _shim.cwt_morlet(x, dt, dj, s0, Jr if J != -1 else -1, wavelet.f0,
+                            want_power=False, want_coef=True)
+    W = np.asarray(W, dtype=np.complex128)
+    # Side outputs pycwt also returns and the reference discards (src/cwt.py:109):
+    # one O(N log N) host FFT, outside the hot path.
+    N = _shim.next_pow2(n0)
+    sft = np.fft.fft(x, N)
+    ftfreqs = 2 * np.pi * np.fft.fftfreq(N, dt)
+    return W, sj, fr, coi, sft[1:N // 2] / N ** 0.5, ftfreqs[1:N // 2] / (2 * np.pi)
+
+
+def _normalised(y, normalize):
+    y = np.asarray(y, dtype=float)
+    return (y - y.mean()) / y.std() if normalize else y
+
+
+def xwt(y1, y2, dt, dj=1 / 12, s0=-1, J=-1, significance_level=0.95, wavelet="morlet", normalize=True):
+    """Cross wavelet transform.  Returns ``(W12, coi, freq, signif)``."""
+    wavelet = _as_morlet(wavelet)
+    y1 = np.asarray(y1, dtype=float)
+    y2 = np.asarray(y2, dtype=float)
+    std1, std2 = y1.std(), y2.std()
+    a, b = _normalised(y1, normalize), _normalised(y2, normalize)
+    Jr, sj, freq, coi = _resolve_s0_J(y1.size, dt, dj, s0, J, wavelet)
+    _, _, W12 = _shim.xwt_wct(a, b, dt, dj, s0, Jr, wavelet.f0, want_wct=False, want_phase=False,
+                              want_w12=True)
+    if normalize:
+        std1 = std2 = 1.0
+    a1, a2 = ar1(y1)[0], ar1(y2)[0]
+    Pk1, Pk2 = ar1_spectrum(freq * dt, a1), ar1_spectrum(freq * dt, a2)
+    dof = wavelet.dofmin
+    signif = std1 * std2 * (Pk1 * Pk2) ** 0.5 * _chi2_ppf(significance_level, dof) / dof
+    return np.asarray(W12, dtype=np.complex128), coi, freq, signif
+
+
+def wct(y1, y2, dt, dj=1 / 12, s0=-1, J=-1, sig=True, significance_level=0.95, wavelet="morlet",
+        normalize=True, **kwargs):
+    """Wavelet coherence.  Returns ``(WCT, aWCT, coi, freq, sig)``.  Unknown
+    keyword arguments are swallowed when ``sig=False`` (the reference relies on
+    that at src/xwt.py:126) and forwarded to ``wct_significance`` otherwise."""
+    wavelet = _as_morlet(wavelet)
+    y1 = np.asarray(y1, dtype=float)
+    y2 = np.asarray(y2, dtype=float)
+    if s0 == -1:
+        s0 = 2 * dt / wavelet.flambda()
+    if J == -1:
+        J = int(np.round(np.log2(y1.size * dt / s0) / dj))
+    a, b = _normalised(y1, normalize), _normalised(y2, normalize)
+    _, _, freq, coi = _resolve_s0_J(y1.size, dt, dj, s0, J, wavelet)
+    WCT, aWCT, _ = _shim.xwt_wct(a, b, dt, dj, s0, J, wavelet.f0, want_wct=True, want_phase=True)
+    if sig:
+        a1, a2 = ar1(y1)[0], ar1(y2)[0]
+        sig = wct_significance(a1, a2, dt=dt, dj=dj, s0=s0, J=J, significance_level=significance_level,
+                               wavelet=wavelet, **kwargs)
+    else:
+        sig = np.asarray([0])
+    return np.asarray(WCT, dtype=float), np.asarray(aWCT, dtype=float), coi, freq, sig
+
+
+def _cache_file(al1, al2, dt, dj, s0, J, level, mc_count, seed, white, wavelet) -> Path:
+    root = Path(os.environ.get("WTB_CACHE_DIR", Path.home() / ".cache" / "wavelet_b200"))
+    key = (f"wct_sig_{al1:.10f}_{al2:.10f}_{dj:.6f}_{s0 / dt:.6f}_{J:d}_{level:.4f}_{mc_count:d}_{seed:d}_"
+           f"{'white' if white else 'ar1'}_{wavelet.name}_{_shim.get_precision()}")
+    return root / f"{key}.gz"
+
+
+def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="morlet", mc_count=300,
+                     progress=True, cache=True, seed=0, white=False, surrogates=None, n_shards=1):
+    """Monte Carlo coherence significance (one value per scale).
+
+    Runs entirely on the GPU: Philox AR(1) surrogates -> CWT -> smoothing ->
+    coherence -> per-scale histograms.  ``cache=True`` stores the result on disk
+    keyed on the exact arguments (pycwt keeps a similar cache under
+    ~/.cache/pycwt).  ``surrogates`` ([mc_count, 2, N]) injects ready-made noise."""
+    wavelet = _as_morlet(wavelet)
+    J = int(J)
+    path = _cache_file(al1, al2, dt, dj, s0, J, significance_level, mc_count, seed, white, wavelet)
+    if cache and surrogates is None:
+        try:
+            return np.loadtxt(path, unpack=True)
+        except OSError:
+            pass
+    _, maxscale = _shim.wct_mc_geometry(dt, dj, s0, J, wavelet.f0)
+    hist = _shim.wct_mc_hist(al1, al2, dt, dj, s0, J, wavelet.f0, mc_first=0, mc_count=mc_count,
+                             seed=seed, surrogates=surrogates, white=white)
+    has = _shim.row_has_points(dt, dj, s0, J, wavelet.f0)
+    sig95 = _shim.wct_sig_from_hist(hist, maxscale, significance_level, has)
+    if cache and surrogates is None:
+        try:
+            path.parent.mkdir(parents=True, exist_ok=True)
+            np.savetxt(path, sig95)
+        except OSError:
+            pass
+    return sig95
+
+
+def rednoise(N, g, a=1.0, seed=0):
+    """AR(1) red noise of length N generated on the GPU (Philox, Box-Muller)."""
+    out = _shim.rednoise(g, g, int(N), 0, 1, seed, f64=True)
+    return out[0, 0] * a

@@ -50,6 +50,9 @@ int  wtb_device_count(void);
 int  wtb_init(int device);
 void wtb_shutdown(void);
 const char *wtb_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's
+ * gpu_launches is the difference across the timed region). */
+uint64_t wtb_kernel_launches(void);
 
 /* ---- CWT: replaces pycwt.cwt (src/cwt.py:110) + |W|^2 (src/cwt.py:114) ---- */
 /* Scales, Fourier frequencies and cone of influence exactly as pycwt.cwt

@@ -1,0 +1,113 @@
+"""Known-answer and algebraic pins for the pycwt restatement (parity unpinned by
+the reference's own tests -- SURVEY.md section 8c -- so the oracle is anchored on
+analytic results and on the AR(1) values measured on the reference's sample data)."""
+
+import numpy as np
+import pytest
+from scipy.signal import convolve2d
+from scipy.stats import chi2
+
+from oracle import pycwt_oracle as po
+
+DT = 1 / 12
+
+
+def test_morlet_constants():
+    m = po.Morlet(6)
+    assert m.flambda() == pytest.approx(1.03304364775, abs=1e-10)
+    assert m.coi() == pytest.approx(2 ** -0.5)
+    assert (m.dofmin, m.cdelta, m.gamma, m.deltaj0) == (2, 0.776, 2.32, 0.60)
+    # no Heaviside step: negative frequencies contribute pi^-1/4 e^-18
+    assert m.psi_ft(0.0) == pytest.approx(np.pi ** -0.25 * np.exp(-18))
+
+
+def test_cwt_shapes_and_axes_cfg1(series):
+    x = series["cpi_value"]
+    W, sj, freqs, coi, fft_, fftfreqs = po.cwt(x, DT, 1 / 12, 2 * DT, 7 / (1 / 12))
+    assert W.shape == (85, 1346) and sj.size == 85 and coi.size == 1346
+    assert fft_.size == fftfreqs.size == 2048 // 2 - 1
+    assert sj[0] == 2 * DT and sj[-1] == pytest.approx(2 * DT * 2 ** 7)
+    assert coi[0] == pytest.approx(coi[-1]) and coi.argmax() in (672, 673)
+
+
+def test_cwt_sinusoid_peaks_at_fourier_period():
+    t = np.arange(2048) * DT
+    for P in (0.5, 2.0, 8.0):
+        W, sj, freqs, *_ = po.cwt(np.cos(2 * np.pi * t / P), DT, 1 / 12, 2 * DT, -1)
+        peak = 1 / freqs[(np.abs(W) ** 2)[:, 1024].argmax()]
+        assert abs(np.log2(peak / P)) <= 1 / 12
+
+
+def test_cwt_white_noise_mean_power_is_variance():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(4096)
+    W = po.cwt(x, DT, 1 / 4, 2 * DT, 24)[0]
+    assert np.mean(np.abs(W[:16]) ** 2) == pytest.approx(1.0, rel=0.1)
+
+
+def test_ar1_on_sample_data(series):
+    assert po.ar1(series["inflation_value"])[0] == pytest.approx(0.9888356230, abs=1e-9)
+    assert po.ar1(series["expectation_value"])[0] == pytest.approx(0.9698623532, abs=1e-9)
+    d = 100 * np.diff(np.log(series["cpi_value"]))
+    assert po.ar1(d)[0] == pytest.approx(0.4705602642, abs=1e-9)
+    with pytest.raises(Warning):
+        po.ar1(series["cpi_value"])          # raw CPI: no upper bound (src/wavelet_plots.py:684 fallback)
+    with pytest.raises(Warning):
+        po.ar1(series["pair_inflation"])
+
+
+def test_ar1_recovers_known_coefficient():
+    rng = np.random.default_rng(1)
+    y = po.rednoise(20000, 0.7, 1, rng)
+    assert po.ar1(y)[0] == pytest.approx(0.7, abs=0.02)
+    assert po.burn_in(0.989) == 181 and po.burn_in(0.966) == 58 and po.burn_in(0.7) == 6
+
+
+def test_significance_closed_form():
+    sj = 2 * DT * 2 ** (np.arange(10) / 2)
+    signif, theor = po.significance(1.0, DT, sj, 0, 0.5, significance_level=0.95)
+    assert po.chi2_ppf_dof2(0.95) == pytest.approx(chi2.ppf(0.95, 2), rel=1e-13)
+    assert np.allclose(signif, theor * chi2.ppf(0.95, 2) / 2)
+    f = DT / (sj * po.Morlet().flambda())
+    assert np.allclose(theor, po.ar1_spectrum(f, 0.5))
+
+
+def test_rect_and_scale_window_semantics():
+    assert np.allclose(po.rect(10, True), np.r_[0.5, np.ones(8), 0.5] / 9)
+    # convolve2d 'same' with an even window: rows i-5 .. i+4, zero fill, no renormalisation
+    T = np.zeros((30, 1)); T[12, 0] = 1
+    out = convolve2d(T, po.rect(10, True)[:, None], "same")[:, 0]
+    assert np.nonzero(out)[0].tolist() == list(range(8, 18))
+    assert out[8] == pytest.approx(0.5 / 9) and out[17] == pytest.approx(0.5 / 9)
+
+
+def test_wct_bounds_and_identities(series):
+    y1, y2 = series["pair_inflation"], series["pair_expectation"]
+    WCT, aWCT, coi, freq, sig = po.wct(y1, y2, DT, dj=1 / 8, s0=2 * DT, J=-1, sig=False)
+    assert WCT.shape == (66, 565) and sig.tolist() == [0]
+    assert WCT.min() >= 0 and WCT.max() <= 1 + 1e-12
+    assert np.abs(po.wct(y1, y1, DT, dj=1 / 8, s0=2 * DT, J=-1, sig=False)[0] - 1).max() < 1e-12
+    W12 = po.xwt(y2, y2, DT, dj=1 / 8, s0=2 * DT, J=-1)[0]
+    W = po.cwt((y2 - y2.mean()) / y2.std(), DT, 1 / 8, 2 * DT, -1)[0]
+    assert np.allclose(W12, np.abs(W) ** 2)
+    # unknown kwargs are swallowed when sig=False (src/xwt.py:126 relies on it)
+    po.wct(y1, y2, DT, delta_j=1 / 8, s0=2 * DT, J=-1, sig=False, cache=True)
+
+
+def test_mc_geometry_cfg3():
+    N, sj, freq, outside, maxscale = po.mc_geometry(DT, 1 / 8, 2 * DT, 65, po.Morlet())
+    assert N == 3351 and maxscale == 65 and outside.all(axis=1).sum() == 0
+    assert outside.mean() == pytest.approx(0.914, abs=1e-3)
+
+
+def test_wct_significance_small_and_histogram_variants():
+    rng = np.random.default_rng(4)
+    sig, hist = po.wct_significance(0.8, 0.6, DT, 1 / 4, 2 * DT, 16, mc_count=3, rng=rng, return_hist=True)
+    assert np.isfinite(sig[:-1]).all() and np.isnan(sig[-1])
+    assert ((sig[:-1] > 0.3) & (sig[:-1] < 1)).all()
+    N, _, _, outside, maxscale = po.mc_geometry(DT, 1 / 4, 2 * DT, 16, po.Morlet())
+    assert hist.sum() == 3 * outside[:maxscale].sum()
+    R2 = np.random.default_rng(0).uniform(0, 1, outside.shape)
+    a = po.coherence_histogram(R2, outside, maxscale, faithful_loop=True)
+    b = po.coherence_histogram(R2, outside, maxscale, faithful_loop=False)
+    assert np.array_equal(a, b)

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "wtb_init": ([_i32], _i32),
     "wtb_shutdown": ([], None),
     "wtb_last_error": ([], C.c_char_p),
+    "wtb_kernel_launches": ([], C.c_uint64),
     "wtb_cwt_axes": ([_i32, _f64, _f64, _f64, _i32, _f64, _pi, _pd, _pd, _pd], _i32),
     "wtb_cwt_morlet": ([_vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp], _i32),
     "wtb_xwt_wct": ([_vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp, _vp], _i32),
@@ -118,6 +119,11 @@ def init(device: int = 0) -> None:
 def shutdown() -> None:
     if _lib is not None:
         _lib.wtb_shutdown()
+
+
+def kernel_launches() -> int:
+    """Kernels launched by the library so far in this process."""
+    return int(lib().wtb_kernel_launches())
 
 
 def device_count() -> int:

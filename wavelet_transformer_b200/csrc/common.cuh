@@ -27,6 +27,14 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     if (e__ != cudaSuccess) return ::wtb::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
 
+// after every kernel launch: count it (wtb_kernel_launches) and surface launch errors
+void note_launch();
+#define WTB_LAUNCH_CHECK()            \
+  do {                                \
+    ::wtb::note_launch();             \
+    WTB_CUDA(cudaGetLastError());     \
+  } while (0)
+
 #define WTB_REQUIRE(cond, code, ...)   \
   do {                                 \
     if (!(cond)) {                     \

@@ -80,7 +80,7 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
-  WTB_CUDA(cudaGetLastError());
+  WTB_LAUNCH_CHECK();
   // enough CTAs to fill the machine for small batches, few forward-FFT re-reads for large ones
   int chunk = S;
   const int64_t want = 4LL * sm_count();
@@ -91,7 +91,7 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   k_cwt_rows<T><<<(unsigned)(batch * nchunks), threads, smem, st>>>(
       d_xhat, n0, N, log2N, S, chunk, d_scales, dt, f0, tw, d_power, d_coef,
       (flags & WTB_COI_MASK) ? 1 : 0, morlet_flambda(f0) / std::sqrt(2.0) * dt, morlet_flambda(f0));
-  WTB_CUDA(cudaGetLastError());
+  WTB_LAUNCH_CHECK();
   return WTB_OK;
 }
 

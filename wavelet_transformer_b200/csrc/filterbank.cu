@@ -312,7 +312,7 @@ static int modwt_impl(const void *x, int64_t batch, int n, const Taps &taps, int
   return run_batched(x, out, batch, sizeof(T) * n, sizeof(T) * (size_t)(J + 1) * n, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
                        k_modwt<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
-                       WTB_CUDA(cudaGetLastError());
+                       WTB_LAUNCH_CHECK();
                        return WTB_OK;
                      });
 }
@@ -325,7 +325,7 @@ static int imodwt_impl(const void *w, int64_t batch, int n, const Taps &taps, in
   return run_batched(w, out, batch, sizeof(T) * (size_t)(J + 1) * n, sizeof(T) * n, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
                        k_imodwt<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
-                       WTB_CUDA(cudaGetLastError());
+                       WTB_LAUNCH_CHECK();
                        return WTB_OK;
                      });
 }
@@ -354,7 +354,7 @@ static int mra_impl(const void *w, int64_t batch, int n, const double *filt, int
   return run_batched(w, out, batch, row, row, flags, st, [&](const void *di, void *dout, int64_t nb) -> int {
     WTB_REQUIRE(nb * (J + 1) < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
     k_modwtmra<T><<<(unsigned)(nb * (J + 1)), threads_for(n), smem, st>>>((const T *)di, n, J, d_filt, d_flen, (T *)dout);
-    WTB_CUDA(cudaGetLastError());
+    WTB_LAUNCH_CHECK();
     return WTB_OK;
   });
 }
@@ -389,7 +389,7 @@ static int wavedec_impl(const void *x, int64_t batch, int n, const Taps &taps, i
   return run_batched(x, coeffs, batch, sizeof(T) * n, sizeof(T) * (size_t)plan.total, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
                        k_wavedec<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, plan, taps, (T *)dout);
-                       WTB_CUDA(cudaGetLastError());
+                       WTB_LAUNCH_CHECK();
                        return WTB_OK;
                      });
 }
@@ -409,7 +409,7 @@ static int waverec_impl(const void *coeffs, int64_t batch, const int *lens, int 
   return run_batched(coeffs, x, batch, sizeof(T) * (size_t)plan.total, sizeof(T) * (size_t)nout, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
                        k_waverec<T><<<(unsigned)nb, threads_for(nout), smem, st>>>((const T *)di, plan, taps, (T *)dout);
-                       WTB_CUDA(cudaGetLastError());
+                       WTB_LAUNCH_CHECK();
                        return WTB_OK;
                      });
 }

@@ -108,7 +108,7 @@ int rednoise_device(double a1, double a2, int nsurr, int64_t first, int64_t coun
   WTB_REQUIRE(count * 2 < (1LL << 31), WTB_EUNSUPPORTED, "too many surrogates in one launch");
   k_rednoise<T><<<(unsigned)(count * 2), kNoiseThreads, 0, st>>>(
       a1, a2, burn_in(a1), burn_in(a2), nsurr, first, seed, white ? 1 : 0, d_out);
-  WTB_CUDA(cudaGetLastError());
+  WTB_LAUNCH_CHECK();
   return WTB_OK;
 }
 template int rednoise_device<float>(double, double, int, int64_t, int64_t, uint64_t, bool, float *, cudaStream_t);

@@ -1,5 +1,6 @@
 // Runtime plumbing of libwavelet_sm100a.so: errors, device binding, scratch
 // arenas, twiddle tables, and the small host-side pieces of the C ABI.
+#include <atomic>
 #include <cstdarg>
 
 #include "common.cuh"
@@ -19,6 +20,10 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   set_error("CUDA error %s (%d) at %s:%d: %s", cudaGetErrorName(e), (int)e, file, line, what);
   return WTB_ECUDA;
 }
+
+static std::atomic<uint64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- device binding -------------------------------------------------------------
 static std::mutex g_mu;
@@ -178,6 +183,8 @@ using namespace wtb;
 extern "C" {
 
 int wtb_version(void) { return 100; }
+
+uint64_t wtb_kernel_launches(void) { return wtb::launches(); }
 
 int wtb_device_count(void) {
   int n = 0;

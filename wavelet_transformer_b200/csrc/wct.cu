@@ -195,10 +195,10 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   WTB_CUDA(cudaFuncSetAttribute(k_wct_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
   WTB_REQUIRE(pairs * S < (1LL << 31) && pairs * 2 < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
   k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
-  WTB_CUDA(cudaGetLastError());
+  WTB_LAUNCH_CHECK();
   k_wct_rows<T><<<(unsigned)(pairs * S), threads, smem_rows, st>>>(
       d_xhat, n0, N, log2N, S, d_scales, dt, f0, tw, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
-  WTB_CUDA(cudaGetLastError());
+  WTB_LAUNCH_CHECK();
   if (smooth) {
     const int64_t cols = pairs * n0;
     const unsigned blocks = (unsigned)((cols + 255) / 256);
@@ -206,7 +206,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
       k_wct_scale<T, 1><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, nullptr, d_hist, d_tlo, d_thi, maxscale);
     else
       k_wct_scale<T, 0><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, d_wct, nullptr, nullptr, nullptr, 0);
-    WTB_CUDA(cudaGetLastError());
+    WTB_LAUNCH_CHECK();
   }
   return WTB_OK;
 }

@@ -1,0 +1,115 @@
+"""Batched and multi-GPU entry points.
+
+One process per GPU (``torch.distributed``); the two shardable units of the hot
+path are independent *series* (fused CWT+power) and independent Monte Carlo
+*realisations* (coherence significance).  Series need no collective at all;
+realisations need exactly one: an integer all-reduce of the per-scale
+histograms, after which every rank holds the same thresholds.
+
+PyTorch is used here only as plumbing (device buffers, streams, NCCL); every
+kernel is in libwavelet_sm100a.so.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _shim
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block [start, stop) of `total` units owned by `rank`; the first
+    ``total % world`` ranks get one extra unit."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    base, extra = divmod(int(total), world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def cwt_power_resident(x, power, dt, dj, s0, J, f0=6.0, generic_only=False):
+    """Fused CWT+power of a device-resident batch.
+
+    x: torch CUDA float32/float64 tensor [batch, n0]; power: preallocated
+    [batch, J+1, n0] tensor of the same dtype.  Enqueued on torch's current
+    stream; nothing is copied or synchronised."""
+    import torch
+    if not (x.is_cuda and power.is_cuda and x.is_contiguous() and power.is_contiguous()):
+        raise ValueError("x and power must be contiguous CUDA tensors")
+    if x.dtype != power.dtype or x.dtype not in (torch.float32, torch.float64):
+        raise ValueError("x and power must both be float32 or both float64")
+    batch, n0 = x.shape
+    if tuple(power.shape) != (batch, int(J) + 1, n0):
+        raise ValueError(f"power must have shape {(batch, int(J) + 1, n0)}")
+    _shim.cwt_power_device(x.data_ptr(), batch, n0, dt, dj, s0, int(J), f0, power.data_ptr(),
+                           f64=x.dtype == torch.float64,
+                           stream=torch.cuda.current_stream().cuda_stream, generic_only=generic_only)
+    return power
+
+
+def wct_hist_resident(hist, a1, a2, dt, dj, s0, J, f0, mc_first, mc_count, seed, f64=False, white=False):
+    """Add the coherence histograms of realisations [mc_first, mc_first+mc_count)
+    to the device int64 tensor `hist` [J+1, 1000] (bit-identical to uint64)."""
+    import torch
+    if not (hist.is_cuda and hist.dtype == torch.int64 and hist.is_contiguous()):
+        raise ValueError("hist must be a contiguous CUDA int64 tensor")
+    if tuple(hist.shape) != (int(J) + 1, _shim.NBINS):
+        raise ValueError(f"hist must have shape {(int(J) + 1, _shim.NBINS)}")
+    _shim.wct_mc_hist_device(a1, a2, dt, dj, s0, int(J), f0, mc_first, mc_count, seed, hist.data_ptr(),
+                             f64=f64, white=white, stream=torch.cuda.current_stream().cuda_stream)
+    return hist
+
+
+def reduce_histogram(hist, group=None):
+    """Sum the per-rank histograms in place over the process group (the only
+    collective of the whole hot path).  `hist` is a torch int64 tensor (CUDA for
+    NCCL, CPU for gloo).  No-op without an initialised process group."""
+    dist = _dist()
+    if dist is not None and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def wct_significance_sharded(a1, a2, dt, dj, s0, J, significance_level=0.95, mc_count=300, seed=0,
+                             f0=6.0, f64=False, white=False, group=None, hist_fn=None, device=None):
+    """Monte Carlo coherence significance with realisations sharded over ranks.
+
+    Every rank computes the histogram of its contiguous block of realisations
+    (Philox streams are keyed by the GLOBAL realisation index, so the sum does
+    not depend on the partition), the histograms are all-reduced, and every rank
+    returns the same ``(sig95[J+1], hist[J+1,1000])``.
+
+    ``hist_fn(first, count) -> int64 array [J+1, 1000]`` replaces the GPU kernel
+    (used by the CPU gloo tests of the sharding / reduction logic)."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank(group) if dist else 0
+    world = dist.get_world_size(group) if dist else 1
+    first, stop = shard_range(mc_count, rank, world)
+    S = int(J) + 1
+    if hist_fn is not None:
+        local = np.asarray(hist_fn(first, stop - first), dtype=np.int64)
+        hist = torch.from_numpy(np.ascontiguousarray(local))
+        if device is not None:
+            hist = hist.to(device)
+    else:
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        hist = torch.zeros((S, _shim.NBINS), dtype=torch.int64, device=dev)
+        if stop > first:
+            wct_hist_resident(hist, a1, a2, dt, dj, s0, J, f0, first, stop - first, seed, f64=f64, white=white)
+    reduce_histogram(hist, group)
+    total = hist.cpu().numpy().astype(np.uint64)
+    sig = significance_from_histogram(total, dt, dj, s0, J, significance_level, f0)
+    return sig, total
+
+
+def significance_from_histogram(hist, dt, dj, s0, J, significance_level=0.95, f0=6.0):
+    """Percentile step of pycwt.wct_significance on an accumulated histogram."""
+    _, maxscale = _shim.wct_mc_geometry(dt, dj, s0, int(J), f0)
+    has = _shim.row_has_points(dt, dj, s0, int(J), f0)
+    return _shim.wct_sig_from_hist(hist, maxscale, significance_level, has)

@@ -225,25 +225,20 @@ def run_gpu(args):
     n0 = CWT["n0"]
 
     def make_series(count, seed):
-        """Unit-variance AR(1) g=0.7 series generated on the device (synthetic cfg4 input)."""
-        g = torch.Generator(device=dev)
-        g.manual_seed(seed)
-        burn = 32
-        eps = torch.randn((count, n0 + burn), generator=g, device=dev, dtype=torch.float32)
-        # y[t] = a*y[t-1] + eps[t] via a blocked scan on the device (input prep, untimed)
-        y = torch.empty_like(eps)
-        prev = torch.zeros(count, device=dev)
-        a = CWT["ar1"]
-        for t in range(n0 + burn):
-            prev = a * prev + eps[:, t]
-            y[:, t] = prev
-        return (y[:, burn:] * (1 - a * a) ** 0.5).contiguous()
+        """Unit-variance AR(1) g=0.7 series generated on the device by the library's own Philox
+        generator (synthetic cfg4 input; counter = global series index, so shards differ)."""
+        pairs = (count + 1) // 2
+        buf = torch.empty((pairs, 2, n0), dtype=torch.float32, device=dev)
+        _shim.rednoise_device(CWT["ar1"], CWT["ar1"], n0, rank * pairs, pairs, seed, buf.data_ptr(),
+                              stream=torch.cuda.current_stream().cuda_stream)
+        y = buf.reshape(pairs * 2, n0)[:count] * (1 - CWT["ar1"] ** 2) ** 0.5
+        return y.contiguous()
 
     # ------------------------------------------------------------------ main workload
     sampler = ClockSampler(local) if rank == 0 else None
     if args.workload == "cwt":
         B = args.series
-        x = make_series(B, 1234 + rank)
+        x = make_series(B, 1234)
         power = torch.empty((B, S, n0), dtype=torch.float32, device=dev)
 
         def step():

@@ -278,6 +278,13 @@ def rednoise(a1, a2, nsurr, first, count, seed, *, f64=False, white=False):
     return out
 
 
+def rednoise_device(a1, a2, nsurr, first, count, seed, out_ptr, *, f64=False, white=False, stream=0):
+    """Device-resident variant of `rednoise`: out_ptr is a device [count, 2, nsurr] buffer."""
+    flags = DEVICE_PTRS | (F64 if f64 else 0) | (NOISE_WHITE if white else 0)
+    _check(lib().wtb_rednoise(a1, a2, nsurr, int(first), int(count), C.c_uint64(int(seed)), flags,
+                              _ptr(int(out_ptr)), C.c_void_p(int(stream))), "wtb_rednoise")
+
+
 # ---------------------------------------------------------------- MODWT / DWT
 def _taps(lo, hi):
     lo = np.ascontiguousarray(lo, dtype=np.float64)

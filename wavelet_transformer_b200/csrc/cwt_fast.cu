@@ -49,27 +49,16 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// step A + twiddle + transpose.  On entry u[br5(k2)] = Y[lane + 32 k2] for k2 < 2^L.
-// On exit u[br5(k1)] = A'[k1][lane] for all 32 k1.
-__device__ __forceinline__ void step_a_transpose(float2 (&u)[32], int L, const float2 *tw, float2 *tr,
-                                                 int lane) {
-  fft32::dit32(u, L);
-#pragma unroll
-  for (int t2 = 0; t2 < 32; ++t2) {
-    const float2 v = cmulf(u[t2], tw[t2 * 32 + lane]);
-    tr[lane * kTrStride + t2] = v;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) u[fft32::br5(k1)] = tr[k1 * kTrStride + lane];
-  __syncwarp();
-}
+constexpr int kMaxRows = 512;          // scale rows staged in shared memory
 
+// One dit32 call site serves the forward transform (s = -1), step A and step B of
+// every scale row: the hot code stays well inside the 32 KB instruction cache.
 __global__ void __launch_bounds__(kWarps * 32, 2)
 k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
                 const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem &sm = *reinterpret_cast<CtaSmem *>(smem_raw);
+  RowParam *srow = reinterpret_cast<RowParam *>(smem_raw + sizeof(CtaSmem));
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
@@ -77,66 +66,90 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
     sincospif(2.0f * (float)((i >> 5) * (i & 31)) / (float)kN, &s, &c);
     sm.tw[i] = make_float2(c, s);
   }
+  for (int i = threadIdx.x; i < S; i += blockDim.x) srow[i] = rows[i];
   __syncthreads();
   WarpSmem &ws = sm.w[warp];
   const float2 *tw = sm.tw;
   const int64_t gwarp = (int64_t)blockIdx.x * kWarps + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  const bool full_row = (n0 == kN);
+  const float lanef = (float)lane;
   float2 u[32];
 
   for (int64_t b = gwarp; b < batch; b += nwarps) {
-    // ---- forward FFT: X^[t] = conj(sum_k x[k] w^(+k t)) for real x
     const float *xr = x + b * n0;
+    float *out = power + b * (int64_t)S * n0 + lane;
+#pragma unroll 1
+    for (int s = -1; s < S; ++s) {
+      int L, two_pass;
+      if (s < 0) {
+        // forward FFT of the real series: X^[t] = conj(sum_k x[k] w^(+k t))
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      const int k = lane + 32 * k2;
-      u[fft32::br5(k2)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, 0.0f);
-    }
-    step_a_transpose(u, 5, tw, ws.tr, lane);
-    fft32::dit32(u, 5);
-#pragma unroll
-    for (int t1 = 0; t1 < 16; ++t1) ws.xhat[lane + 32 * t1] = make_float2(u[t1].x, -u[t1].y);
-    __syncwarp();
-
-    float *out = power + b * (int64_t)S * n0;
-    for (int s = 0; s < S; ++s) {
-      const RowParam rp = rows[s];
-      int L;
-      if (rp.multi) {
-        const int K2 = 1 << rp.L;
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) {
-          if (k2 < K2) {
-            const int k = lane + 32 * k2;
-            const float z = fmaf(rp.a, (float)k, -f0);
-            const float d = rp.norm * __expf(-0.5f * z * z);
-            const float2 v = ws.xhat[k];
-            u[fft32::br5(k2)] = make_float2(v.x * d, v.y * d);
-          }
+        for (int k2 = 0; k2 < 32; ++k2) {
+          const int k = lane + 32 * k2;
+          u[fft32::br5(k2)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, 0.0f);
         }
-        step_a_transpose(u, rp.L, tw, ws.tr, lane);
         L = 5;
+        two_pass = 1;
       } else {
-        {
-          const float z = fmaf(rp.a, (float)lane, -f0);
-          const float d = rp.norm * __expf(-0.5f * z * z);
+        const RowParam rp = srow[s];
+        L = rp.L;
+        two_pass = rp.multi;
+        const float zl = fmaf(rp.a, lanef, -f0);   // s*w_k - f0 at k = lane
+        if (two_pass) {
+          const int K2 = 1 << rp.L;
+          const float a32 = rp.a * 32.0f;
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            if (k2 < K2) {
+              const float z = fmaf(a32, (float)k2, zl);
+              const float d = rp.norm * __expf(-0.5f * z * z);
+              const float2 v = ws.xhat[lane + 32 * k2];
+              u[fft32::br5(k2)] = make_float2(v.x * d, v.y * d);
+            }
+          }
+        } else {
+          const float d = rp.norm * __expf(-0.5f * zl * zl);
           const float2 v = ws.xhat[lane];
           ws.y[lane] = make_float2(v.x * d, v.y * d);
+          __syncwarp();
+          const int K1 = 1 << rp.L;
+#pragma unroll
+          for (int k1 = 0; k1 < 32; ++k1)
+            if (k1 < K1) u[fft32::br5(k1)] = cmulf(ws.y[k1], tw[k1 * 32 + lane]);
+          __syncwarp();
         }
-        __syncwarp();
-        const int K1 = 1 << rp.L;
-#pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1)
-          if (k1 < K1) u[fft32::br5(k1)] = cmulf(ws.y[k1], tw[k1 * 32 + lane]);
-        __syncwarp();
-        L = rp.L;
       }
-      fft32::dit32(u, L);
-      float *orow = out + (int64_t)s * n0 + lane;
+#pragma unroll 1
+      for (;;) {
+        fft32::dit32(u, L);
+        if (!two_pass) break;
+        // step A done (lane = k1): twiddle by w1024^(k1 t2), transpose, reload with lane = t2
 #pragma unroll
-      for (int t1 = 0; t1 < 32; ++t1) {
-        const float p = fmaf(u[t1].x, u[t1].x, u[t1].y * u[t1].y);
-        if (lane + 32 * t1 < n0) __stcs(orow + 32 * t1, p);
+        for (int t2 = 0; t2 < 32; ++t2)
+          ws.tr[lane * kTrStride + t2] = cmulf(u[t2], tw[t2 * 32 + lane]);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) u[fft32::br5(k1)] = ws.tr[k1 * kTrStride + lane];
+        __syncwarp();
+        L = 5;
+        two_pass = 0;
+      }
+      if (s < 0) {
+#pragma unroll
+        for (int t1 = 0; t1 < 16; ++t1) ws.xhat[lane + 32 * t1] = make_float2(u[t1].x, -u[t1].y);
+        __syncwarp();
+      } else {
+        float *orow = out + (int64_t)s * n0;
+        if (full_row) {
+#pragma unroll
+          for (int t1 = 0; t1 < 32; ++t1)
+            __stcs(orow + 32 * t1, fmaf(u[t1].x, u[t1].x, u[t1].y * u[t1].y));
+        } else {
+#pragma unroll
+          for (int t1 = 0; t1 < 32; ++t1)
+            if (lane + 32 * t1 < n0) __stcs(orow + 32 * t1, fmaf(u[t1].x, u[t1].x, u[t1].y * u[t1].y));
+        }
       }
     }
   }
@@ -171,7 +184,8 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
   RowParam *d_rows = (RowParam *)scratch;
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
   // rows.data() is pageable: the copy is staged before the call returns
-  const size_t smem = sizeof(CtaSmem);
+  if (S > kMaxRows) return 1;
+  const size_t smem = sizeof(CtaSmem) + sizeof(RowParam) * S;
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ctas_needed = (batch + kWarps - 1) / kWarps;
   const int grid = (int)std::min<int64_t>(ctas_needed, 2LL * sm_count());

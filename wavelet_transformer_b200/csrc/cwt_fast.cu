@@ -11,6 +11,10 @@
 //   step B (lane = t2): x[t2+32t1] = sum_k1 A'[k1][t2] w32^(k1 t1)
 // Lanes map to t2, so for each t1 the warp stores 32 consecutive floats.
 //
+// Arithmetic is the sm_100a packed FP32x2 pipe (FFMA2/FADD2/FMUL2): registers hold
+// (element p, element p+16) pairs in structure-of-arrays form (fft32_gen.cuh), so
+// one instruction does two butterflies / two twiddle products / two |w|^2.
+//
 // Work that the Morlet daughter makes unnecessary is skipped exactly (to 1e-6 of
 // the daughter peak, far inside the FP32 tolerance): negative frequencies, and
 // bins above k_hi(s) = (f0 + 5.3) N dt / (2 pi s).  Rows with k_hi < 32 need no
@@ -22,59 +26,78 @@ namespace wtb {
 
 namespace {
 
+using fft32::add2;
+using fft32::bc;
+using fft32::br4;
+using fft32::fma2;
+using fft32::mul2;
+
 constexpr int kN = 1024;
-constexpr int kWarps = 8;             // warps per CTA
-constexpr int kTrStride = 33;         // padded row of the transpose buffer (float2 units)
+constexpr int kWarps = 16;            // warps per CTA, one CTA per SM
+constexpr int kTrStride = 34;         // floats per row of the transpose buffer (even, == 2 mod 32)
 constexpr float kZCut = 5.3f;         // daughter dropped where |s*w - f0| > kZCut  (exp(-14) ~ 8e-7)
+constexpr int kMaxRows = 256;         // scale rows staged in shared memory
 
 struct RowParam {
-  float a;      // (s/dt) * 2*pi/N : s*w_k = a*k
-  float norm;   // sqrt(2*pi*s/dt) * pi^-1/4 / N
-  int L;        // log2(#non-zero inputs) of the first DFT that runs (step A if multi, else step B)
-  int multi;    // 1: k_hi >= 32 -> step A + transpose + full step B
+  float a;         // (s/dt) * 2*pi/N : s*w_k = a*k
+  float lognorm;   // log2( sqrt(2*pi*s/dt) * pi^-1/4 / N )
+  int L;           // log2(#non-zero inputs) of the first DFT that runs (>= 1)
+  int multi;       // 1: k_hi >= 32 -> step A + transpose + full step B
 };
 
 struct WarpSmem {
-  float2 xhat[kN / 2];              // X^[k], k < 512
-  float2 tr[32 * kTrStride];        // transpose buffer
-  float2 y[32];                     // Y[k] of a single-pass row
+  float2 xr[8][32];                 // xr[m][lane] = Re X^[lane + 32*(2m)], Re X^[lane + 32*(2m+1)]
+  float2 xi[8][32];
+  float trr[32 * kTrStride];        // transpose buffer, real parts:  [k1][2*(t2&15) + (t2>>4)]
+  float tri[32 * kTrStride];
+  float yr[32];                     // Y[k] of a single-pass row
+  float yi[32];
 };
 
 struct CtaSmem {
-  float2 tw[32 * 32];               // tw[a*32+b] = exp(+2*pi*i*a*b/1024)  (symmetric)
+  // exp(+2*pi*i*a*b/1024) tables, float4 = (re_0, re_1, im_0, im_1) for a packed pair
+  float4 tw_a[16][32];              // pair (t2, t2+16) x k1=lane   : step A output twiddle
+  float4 tw_b[16][32];              // pair (2m, 2m+1)  x t2=lane   : single-pass input twiddle
+  RowParam row[kMaxRows];
   WarpSmem w[kWarps];
 };
 
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-constexpr int kMaxRows = 512;          // scale rows staged in shared memory
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
 // One dit32 call site serves the forward transform (s = -1), step A and step B of
-// every scale row: the hot code stays well inside the 32 KB instruction cache.
-__global__ void __launch_bounds__(kWarps * 32, 2)
+// every scale row: the hot code stays inside the instruction cache.
+__global__ void __launch_bounds__(kWarps * 32, 1)
 k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
                 const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem &sm = *reinterpret_cast<CtaSmem *>(smem_raw);
-  RowParam *srow = reinterpret_cast<RowParam *>(smem_raw + sizeof(CtaSmem));
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
-    float s, c;
-    sincospif(2.0f * (float)((i >> 5) * (i & 31)) / (float)kN, &s, &c);
-    sm.tw[i] = make_float2(c, s);
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int p = i >> 5, l = i & 31;
+    float s0, c0, s1, c1;
+    sincospif(2.0f * (float)(p * l) / (float)kN, &s0, &c0);
+    sincospif(2.0f * (float)((p + 16) * l) / (float)kN, &s1, &c1);
+    sm.tw_a[p][l] = make_float4(c0, c1, s0, s1);
+    sincospif(2.0f * (float)(2 * p * l) / (float)kN, &s0, &c0);
+    sincospif(2.0f * (float)((2 * p + 1) * l) / (float)kN, &s1, &c1);
+    sm.tw_b[p][l] = make_float4(c0, c1, s0, s1);
   }
-  for (int i = threadIdx.x; i < S; i += blockDim.x) srow[i] = rows[i];
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sm.row[i] = rows[i];
   __syncthreads();
   WarpSmem &ws = sm.w[warp];
-  const float2 *tw = sm.tw;
   const int64_t gwarp = (int64_t)blockIdx.x * kWarps + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
   const bool full_row = (n0 == kN);
   const float lanef = (float)lane;
-  float2 u[32];
+  const int tidx = 2 * (lane & 15) + (lane >> 4);   // column of this lane (as t2) in the transpose buffer
+  float2 R[16], I[16];
 
   for (int64_t b = gwarp; b < batch; b += nwarps) {
     const float *xr = x + b * n0;
@@ -85,70 +108,107 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
       if (s < 0) {
         // forward FFT of the real series: X^[t] = conj(sum_k x[k] w^(+k t))
 #pragma unroll
-        for (int k2 = 0; k2 < 32; ++k2) {
-          const int k = lane + 32 * k2;
-          u[fft32::br5(k2)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, 0.0f);
+        for (int m = 0; m < 16; ++m) {
+          const int k = lane + 64 * m;
+          R[br4(m)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, k + 32 < n0 ? __ldg(xr + k + 32) : 0.0f);
+          I[br4(m)] = make_float2(0.0f, 0.0f);
         }
         L = 5;
         two_pass = 1;
       } else {
-        const RowParam rp = srow[s];
+        const RowParam rp = sm.row[s];
         L = rp.L;
         two_pass = rp.multi;
         const float zl = fmaf(rp.a, lanef, -f0);   // s*w_k - f0 at k = lane
         if (two_pass) {
-          const int K2 = 1 << rp.L;
-          const float a32 = rp.a * 32.0f;
+          // Y[lane + 32 k2] = X^ * daughter for k2 < 2^L, two k2 per packed op
+          const int M = 1 << (rp.L - 1);
+          const float2 zl2 = make_float2(zl, fmaf(rp.a, 32.0f, zl));
+          const float2 a64 = bc(rp.a * 64.0f);
+          const float2 ln2 = bc(rp.lognorm);
 #pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2) {
-            if (k2 < K2) {
-              const float z = fmaf(a32, (float)k2, zl);
-              const float d = rp.norm * __expf(-0.5f * z * z);
-              const float2 v = ws.xhat[lane + 32 * k2];
-              u[fft32::br5(k2)] = make_float2(v.x * d, v.y * d);
+          for (int m = 0; m < 8; ++m) {
+            if (m < M) {
+              const float2 z = fma2(a64, bc((float)m), zl2);
+              const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);   // -0.5*log2(e)*z^2 + log2(norm)
+              const float2 d = make_float2(ex2(e.x), ex2(e.y));
+              R[br4(m)] = mul2(ws.xr[m][lane], d);
+              I[br4(m)] = mul2(ws.xi[m][lane], d);
             }
           }
         } else {
-          const float d = rp.norm * __expf(-0.5f * zl * zl);
-          const float2 v = ws.xhat[lane];
-          ws.y[lane] = make_float2(v.x * d, v.y * d);
+          const float e = fmaf(zl * zl, -0.72134752044f, rp.lognorm);
+          const float d = ex2(e);
+          const float2 vr = ws.xr[0][lane], vi = ws.xi[0][lane];
+          ws.yr[lane] = vr.x * d;
+          ws.yi[lane] = vi.x * d;
           __syncwarp();
-          const int K1 = 1 << rp.L;
+          // u[k1] = Y[k1] * w1024^(k1 * lane) for k1 < 2^L, two k1 per packed op
+          const int M = 1 << (rp.L - 1);
 #pragma unroll
-          for (int k1 = 0; k1 < 32; ++k1)
-            if (k1 < K1) u[fft32::br5(k1)] = cmulf(ws.y[k1], tw[k1 * 32 + lane]);
+          for (int m = 0; m < 16; ++m) {
+            if (m < M) {
+              const float2 yr = *reinterpret_cast<const float2 *>(&ws.yr[2 * m]);
+              const float2 yi = *reinterpret_cast<const float2 *>(&ws.yi[2 * m]);
+              const float4 t = sm.tw_b[m][lane];
+              const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
+              R[br4(m)] = fma2(yi, neg2(twi), mul2(yr, twr));
+              I[br4(m)] = fma2(yr, twi, mul2(yi, twr));
+            }
+          }
           __syncwarp();
         }
       }
 #pragma unroll 1
       for (;;) {
-        fft32::dit32(u, L);
+        fft32::dit32(R, I, L);
         if (!two_pass) break;
         // step A done (lane = k1): twiddle by w1024^(k1 t2), transpose, reload with lane = t2
 #pragma unroll
-        for (int t2 = 0; t2 < 32; ++t2)
-          ws.tr[lane * kTrStride + t2] = cmulf(u[t2], tw[t2 * 32 + lane]);
+        for (int p = 0; p < 16; ++p) {
+          const float4 t = sm.tw_a[p][lane];
+          const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
+          const float2 vr = fma2(I[p], neg2(twi), mul2(R[p], twr));
+          const float2 vi = fma2(R[p], twi, mul2(I[p], twr));
+          *reinterpret_cast<float2 *>(&ws.trr[lane * kTrStride + 2 * p]) = vr;
+          *reinterpret_cast<float2 *>(&ws.tri[lane * kTrStride + 2 * p]) = vi;
+        }
         __syncwarp();
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) u[fft32::br5(k1)] = ws.tr[k1 * kTrStride + lane];
+        for (int m = 0; m < 16; ++m) {
+          R[br4(m)] = make_float2(ws.trr[(2 * m) * kTrStride + tidx], ws.trr[(2 * m + 1) * kTrStride + tidx]);
+          I[br4(m)] = make_float2(ws.tri[(2 * m) * kTrStride + tidx], ws.tri[(2 * m + 1) * kTrStride + tidx]);
+        }
         __syncwarp();
         L = 5;
         two_pass = 0;
       }
       if (s < 0) {
+        // X^[lane + 32 t1] = conj(u[t1]), t1 < 16 (positive frequencies only)
+        float *pr = reinterpret_cast<float *>(&ws.xr[0][0]);
+        float *pi = reinterpret_cast<float *>(&ws.xi[0][0]);
 #pragma unroll
-        for (int t1 = 0; t1 < 16; ++t1) ws.xhat[lane + 32 * t1] = make_float2(u[t1].x, -u[t1].y);
+        for (int t1 = 0; t1 < 16; ++t1) {
+          pr[(t1 >> 1) * 64 + lane * 2 + (t1 & 1)] = R[t1].x;
+          pi[(t1 >> 1) * 64 + lane * 2 + (t1 & 1)] = -I[t1].x;
+        }
         __syncwarp();
       } else {
         float *orow = out + (int64_t)s * n0;
         if (full_row) {
 #pragma unroll
-          for (int t1 = 0; t1 < 32; ++t1)
-            __stcs(orow + 32 * t1, fmaf(u[t1].x, u[t1].x, u[t1].y * u[t1].y));
+          for (int p = 0; p < 16; ++p) {
+            const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+            __stcs(orow + 32 * p, pw.x);
+            __stcs(orow + 32 * (p + 16), pw.y);
+          }
         } else {
 #pragma unroll
-          for (int t1 = 0; t1 < 32; ++t1)
-            if (lane + 32 * t1 < n0) __stcs(orow + 32 * t1, fmaf(u[t1].x, u[t1].x, u[t1].y * u[t1].y));
+          for (int p = 0; p < 16; ++p) {
+            const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+            if (lane + 32 * p < n0) __stcs(orow + 32 * p, pw.x);
+            if (lane + 32 * (p + 16) < n0) __stcs(orow + 32 * (p + 16), pw.y);
+          }
         }
       }
     }
@@ -159,36 +219,36 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                  int flags, float *d_power, cudaStream_t st) {
-  if (nfft != kN || (flags & WTB_COI_MASK) || f0 < 1.0) return 1;
   const int S = ax.J + 1;
+  if (nfft != kN || (flags & WTB_COI_MASK) || f0 < 1.0 || S > kMaxRows) return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
     int khi = (int)std::floor((f0 + kZCut) / a);
     if (khi > kN / 2 - 1) khi = kN / 2 - 1;
-    if (khi < 0) khi = 0;
+    if (khi < 1) khi = 1;
     RowParam &r = rows[s];
     r.a = (float)a;
-    r.norm = (float)(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / kN);
+    r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / kN);
     if (khi >= 32) {
       r.multi = 1;
       r.L = ilog2(khi / 32 + 1);       // K2 = 2^L >= ceil((khi+1)/32), at most 16 (one-sided)
       if (r.L > 4) r.L = 4;
+      if (r.L < 1) r.L = 1;
     } else {
       r.multi = 0;
-      r.L = ilog2(khi + 1);            // K1 = 2^L >= khi+1
+      r.L = ilog2(khi + 1);            // K1 = 2^L >= khi+1, at least 2
     }
   }
   void *scratch = nullptr;
   WTB_TRY(arena_reserve(sizeof(RowParam) * S, &scratch));
   RowParam *d_rows = (RowParam *)scratch;
-  WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
   // rows.data() is pageable: the copy is staged before the call returns
-  if (S > kMaxRows) return 1;
-  const size_t smem = sizeof(CtaSmem) + sizeof(RowParam) * S;
+  WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
+  const size_t smem = sizeof(CtaSmem);
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ctas_needed = (batch + kWarps - 1) / kWarps;
-  const int grid = (int)std::min<int64_t>(ctas_needed, 2LL * sm_count());
+  const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count());
   k_cwt_fast_1024<<<grid, kWarps * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
   WTB_LAUNCH_CHECK();
   return WTB_OK;

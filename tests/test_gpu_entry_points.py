@@ -1,0 +1,186 @@
+"""GPU: the re-authored reference entry points (src/cwt.py, src/wct.py, src/xwt.py,
+src/dwt.py, src/modwt.py) end to end, against the same pipeline built from the oracle.
+These read like the reference's own tests (tests/test_cwt.py, test_xwt.py, test_dwt.py)
+with the network fetches replaced by the sample_data fixtures and values -- not only
+shapes -- asserted."""
+
+import numpy as np
+import pytest
+
+from oracle import modwt_oracle as mo
+from oracle import pycwt_oracle as po
+from oracle import pywt_oracle as pw
+
+pytestmark = pytest.mark.gpu
+
+DT = 1 / 12
+
+
+@pytest.fixture(autouse=True)
+def _engine(shim, tmp_path, monkeypatch):
+    monkeypatch.setenv("WTB_CACHE_DIR", str(tmp_path))
+    shim.set_precision("fp64")
+    yield
+
+
+def _dates(days):
+    return days.astype("datetime64[D]")
+
+
+def test_run_cwt_matches_reference_pipeline(series):
+    from src import cwt
+    from src.utils.wavelet_helpers import standardize_series
+    y = 100 * np.diff(np.log(series["cpi_value"]))          # the app's AR(1)-bounded fallback series
+    t = _dates(series["cpi_days"])[1:]
+    data = cwt.DataForCWT(t, y, cwt.MOTHER, cwt.DT, cwt.DJ, cwt.S0, cwt.LEVELS)
+    res = cwt.run_cwt(data, standardize=True, detrend=True)
+    assert len(data.time_range) == len(t)                    # reference tests/test_cwt.py:30
+    assert len(res.power) == len(res.period) == 85           # reference tests/test_cwt.py:34
+    dat = standardize_series(y, detrend=True)
+    alpha = po.ar1(y)[0]
+    W, sj, freqs, coi, _, _ = po.cwt(dat, DT, 1 / 12, 2 * DT, 84.0)
+    power = np.abs(W) ** 2
+    signif, _ = po.significance(1.0, DT, sj, 0, alpha, significance_level=0.95)
+    assert np.abs(res.power - power).max() <= 1e-10 * power.max()
+    assert np.allclose(res.period, 1 / freqs, rtol=1e-13)
+    assert np.allclose(res.coi, coi, rtol=1e-13)
+    assert np.abs(res.significance_levels - power / signif[:, None]).max() <= 1e-9 * (power / signif[:, None]).max()
+    assert cwt.run_cwt(data, calculate_significance=False).significance_levels is None
+
+
+def test_run_cwt_raises_warning_for_unbounded_ar1(series):
+    from src import cwt
+    data = cwt.DataForCWT(_dates(series["cpi_days"]), series["cpi_value"], cwt.MOTHER, cwt.DT, cwt.DJ,
+                          cwt.S0, cwt.LEVELS)
+    with pytest.raises(Warning):                             # caught by the app at wavelet_plots.py:684
+        cwt.run_cwt(data)
+
+
+def test_run_cwt_fp32_mode(series, shim):
+    from src import cwt
+    shim.set_precision("fp32")
+    y = 100 * np.diff(np.log(series["cpi_value"]))
+    data = cwt.DataForCWT(_dates(series["cpi_days"])[1:], y, cwt.MOTHER, cwt.DT, cwt.DJ, cwt.S0, cwt.LEVELS)
+    res = cwt.run_cwt(data)
+    power = np.abs(po.cwt(y, DT, 1 / 12, 2 * DT, 84.0)[0]) ** 2
+    assert res.power.dtype == np.float64
+    assert np.abs(res.power - power).max() <= 1e-4 * power.max()
+
+
+def test_run_wct_without_significance(series):
+    from src import wct
+    from src.utils.wavelet_helpers import standardize_series
+    y1 = standardize_series(series["pair_inflation"], detrend=False, remove_mean=True)
+    y2 = standardize_series(series["pair_expectation"], detrend=True, remove_mean=False)
+    data = wct.DataForWCT(y1, y2, wct.MOTHER_DICT[wct.MOTHER], wct.DT, wct.DJ, wct.S0, wct.LEVELS)
+    res = wct.run_wct(data, calculate_signficance=False)
+    WCT, aWCT, coi, freq, sig = po.wct(y1, y2, DT, dj=1 / 8, s0=2 * DT, J=-1, sig=False)
+    assert res.coherence.shape == (66, 565)
+    assert np.abs(res.coherence - WCT).max() <= 1e-10
+    assert np.allclose(res.period, 1 / freq) and np.allclose(res.coi, coi)
+    u, v = np.cos(0.5 * np.pi - aWCT), np.sin(0.5 * np.pi - aWCT)
+    assert np.abs(res.phase_diff_u - u).max() <= 1e-8 and np.abs(res.phase_diff_v - v).max() <= 1e-8
+    with np.errstate(divide="ignore"):
+        assert np.isinf(res.significance_levels).all()      # coherence / [0], as in the reference
+
+
+def test_run_wct_with_monte_carlo_significance(series):
+    """cfg3 end to end: 300-realisation AR(1) Monte Carlo on device (FP64 engine)."""
+    from src import wct
+    y1 = (100 * np.diff(np.log(series["cpi_value"])))[-565:]   # AR(1)-bounded stand-in (the app's fallback)
+    y2 = series["expectation_value"]
+    data = wct.DataForWCT(y1, y2, wct.MOTHER_DICT[wct.MOTHER], wct.DT, wct.DJ, wct.S0, wct.LEVELS)
+    res = wct.run_wct(data, calculate_signficance=True, significance_level=0.95)
+    sig_ratio = res.significance_levels
+    assert sig_ratio.shape == (66, 565)
+    signif = res.coherence[:, 0] / sig_ratio[:, 0]
+    assert np.isnan(signif[-1]) and np.isfinite(signif[:-1]).all()
+    assert ((signif[:-1] > 0.5) & (signif[:-1] < 1.0)).all()
+    ref = po.wct_significance(po.ar1(y1)[0], po.ar1(y2)[0], DT, 1 / 8, 2 * DT, 65, mc_count=40,
+                              rng=np.random.default_rng(3))
+    assert np.abs(signif[:60] - ref[:60]).max() < 0.08       # Monte Carlo error of the 40-run reference
+    # second call is served from the on-disk cache and is identical
+    res2 = wct.run_wct(data, calculate_signficance=True, significance_level=0.95)
+    assert np.array_equal(res2.significance_levels, res.significance_levels, equal_nan=True)
+
+
+def test_run_xwt(series):
+    from src import xwt
+    y1, y2 = series["expectation_value"], (100 * np.diff(np.log(series["cpi_value"])))[-565:]
+    data = xwt.DataForXWT(y1, y2, xwt.MOTHER_DICT[xwt.MOTHER], xwt.DT, xwt.DJ, xwt.S0, xwt.LEVELS)
+    res = xwt.run_xwt(data)
+    assert len(data.t_values) == 565                         # reference tests/test_xwt.py:48
+    assert len(res.power) < len(y1)                          # reference tests/test_xwt.py:53
+    W12, coi, freq, signif = po.xwt(y1, y2, DT, dj=1 / 8, s0=2 * DT)
+    power = np.abs(W12) ** 2
+    assert np.abs(res.power - power).max() <= 1e-10 * power.max()
+    assert np.abs(res.significance_levels - power / signif[:, None]).max() <= 1e-9 * (power / signif[:, None]).max()
+    assert res.coi.size == 565 + 4 and res.coi.min() >= np.log2(xwt.LEVELS[2])
+    # the phase plane comes from the inner wct at pycwt's default dj = 1/12 (delta_j= is swallowed)
+    a = po.wct(y1, y2, DT, s0=2 * DT, J=-1, sig=False)[1]
+    assert res.phase_diff_u.shape == a.shape and a.shape[0] != res.power.shape[0]
+    assert np.abs(res.phase_diff_u - np.cos(0.5 * np.pi - a)).max() <= 1e-8
+
+
+def test_run_dwt_and_smoothing(series):
+    from src import dwt
+    y = series["expectation_value"]                          # odd length (565), like tests/test_regression.py:75
+    data = dwt.DataForDWT(y, dwt.MOTHER)
+    res = dwt.run_dwt(data)
+    assert data.levels is None and res.levels == 6           # reference tests/test_dwt.py:36-42
+    ref = pw.wavedec(y, "db4")
+    assert [len(c) for c in res.coeffs] == [15, 15, 24, 41, 76, 146, 286]
+    for a, b in zip(res.coeffs, ref):
+        assert np.abs(a - b).max() <= 1e-10
+    res.smooth_signal(y, dwt.MOTHER)
+    assert len(res.smoothed_signal_dict[res.levels]["signal"]) == len(y)    # tests/test_dwt.py:48-50
+    for l in (1, 3, 6):
+        kept = [c.copy() for c in ref]
+        for c in range(1, l + 1):
+            kept[-c][:] = 0
+        assert np.abs(res.smoothed_signal_dict[l]["signal"] - pw.waverec(kept, "db4")[1:]).max() <= 1e-10
+    comp = dwt.reconstruct_signal_component(res.coeffs, dwt.MOTHER, 2)
+    only = [c if i == 2 else np.zeros_like(c) for i, c in enumerate(ref)]
+    assert np.abs(comp - pw.waverec(only, "db4")).max() <= 1e-10
+    full = sum(dwt.reconstruct_signal_component(res.coeffs, dwt.MOTHER, i) for i in range(7))
+    assert np.abs(full[:-1] - y).max() <= 1e-9
+
+
+def test_pywt_facade_functions(series):
+    from wavelet_transformer_b200 import pywt_compat as pywt
+    y = series["inflation_value"]
+    assert pywt.dwt_max_level(len(y), pywt.Wavelet("db4").dec_len) == 7
+    c = pywt.wavedec(y, "sym4", level=3)
+    r = pw.wavedec(y, "sym4", level=3)
+    assert all(np.abs(a - b).max() <= 1e-10 for a, b in zip(c, r))
+    cA, cD = pywt.dwt(y, "db2")
+    assert np.abs(pywt.idwt(cA, cD, "db2")[: len(y)] - y).max() <= 1e-10
+    with pytest.raises(NotImplementedError):
+        pywt.wavedec(y, "db4", mode="periodization")
+
+
+def test_modwt_module(series, modwt_golden):
+    from src import modwt
+    for name, filt in (("inflation", "sym4"), ("expectation", "db4")):
+        x = series[f"{name}_value"]
+        w = modwt.modwt(x, filt, 6)
+        assert np.abs(w - modwt_golden[f"{name}|{filt}|modwt"]).max() <= 1e-10 * np.abs(x).max()
+        assert np.abs(modwt.imodwt(w, filt) - x).max() <= 1e-9
+        mra = modwt.modwtmra(w, filt)
+        assert np.abs(mra - modwt_golden[f"{name}|{filt}|mra"]).max() <= 1e-10 * np.abs(x).max()
+        sm = modwt.smooth_signal(w, filt, 6)
+        assert np.abs(sm[6]["signal"] - modwt_golden[f"{name}|{filt}|smooth6"]).max() <= 1e-10 * np.abs(x).max()
+        assert np.abs(sm[1]["signal"] - modwt_golden[f"{name}|{filt}|smooth1"]).max() <= 1e-10 * np.abs(x).max()
+        assert np.array_equal(sm[3]["coeffs"][:3], np.zeros((3, x.size)))
+
+
+def test_pycwt_facade_cwt_side_outputs(series):
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    x = series["expectation_value"]
+    W, sj, fr, coi, fft_, fftfreqs = wavelet.cwt(x, DT, 1 / 12, 2 * DT, 7 / (1 / 12), wavelet.Morlet(6))
+    Wo, sjo, fro, coio, ffto, fqo = po.cwt(x, DT, 1 / 12, 2 * DT, 7 / (1 / 12))
+    assert W.dtype == np.complex128 and np.abs(W - Wo).max() <= 1e-10 * np.abs(Wo).max()
+    assert np.allclose(sj, sjo) and np.allclose(fr, fro) and np.allclose(coi, coio)
+    assert np.allclose(fft_, ffto) and np.allclose(fftfreqs, fqo)
+    with pytest.raises(NotImplementedError):
+        wavelet.cwt(x, DT, wavelet="paul")

@@ -40,6 +40,14 @@ CWT = dict(n0=1024, dj=1 / 12, s0=2 * DT, J=119, f0=6.0, ar1=0.7)
 MC = dict(a1=0.989, a2=0.966, dj=1 / 8, s0=2 * DT, J=65, f0=6.0, seed=2024)
 
 
+def measured_traffic_per_series():
+    """DRAM bytes per series of the dominant kernel from the committed ncu capture (or None)."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["dram_bytes_per_series"])
+    return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -355,7 +363,11 @@ def run_gpu(args):
     if args.workload == "cwt":
         achieved = alg_bytes / per_launch_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": args.traffic_bytes,
+                    "frac": achieved / hbm_peak,
+                    "traffic": (args.traffic_bytes if args.traffic_bytes is not None else
+                                (measured_traffic_per_series() or 0) * args.series or None),
+                    "traffic_source": "profiles/r1_traffic.json: dram read+write bytes per series from one "
+                                      "ncu --set full capture, scaled to this launch's series count",
                     "peak_source": peak_src, "kernel": "fused CWT+power (one launch per step)",
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "fp32": {"algorithmic_flop_per_launch": alg_flops,
@@ -393,7 +405,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cwt", choices=["cwt", "wct_mc"])

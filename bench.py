@@ -204,6 +204,12 @@ def run_gpu(args):
 
     from wavelet_transformer_b200 import _shim, engine
 
+    # Only the JSON line may reach stdout: route everything libraries print (NCCL's version
+    # banner, warnings) to stderr and keep a private handle on the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -396,7 +402,8 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_budget)
         line["cpu_baseline"]["host_cpus"] = os.cpu_count()
-    print(json.dumps(line))
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

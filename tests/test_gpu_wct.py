@@ -142,3 +142,45 @@ def test_mc_device_rng_distribution(shim):
     ref = po.wct_significance(0.8, 0.6, DT, dj, s0, J, mc_count=120, rng=np.random.default_rng(5))
     m = maxscale - 2  # the last rows have very few reliable samples
     assert np.abs(sig[:m] - ref[:m]).max() < 0.05, np.abs(sig[:m] - ref[:m])
+
+
+def test_wct_fp32_n4096_fast_path(shim):
+    """nfft = 4096 takes the register-FFT row kernel (wct_fast.cu); check it against the
+    oracle and against the generic kernels on the cfg5 surrogate shape (n0 = 3351)."""
+    rng = np.random.default_rng(41)
+    n0 = 3351
+    y1 = np.stack([_norm(po.rednoise(n0, 0.989, 1, rng)) for _ in range(2)])
+    y2 = np.stack([_norm(po.rednoise(n0, 0.966, 1, rng)) for _ in range(2)])
+    wct, phase, w12 = shim.xwt_wct(y1, y2, DT, 1 / 8, 2 * DT, 65, f64=False, want_w12=True)
+    wct_g, phase_g, w12_g = shim.xwt_wct(y1, y2, DT, 1 / 8, 2 * DT, 65, f64=False, want_w12=True,
+                                         generic_only=True)
+    for b in range(2):
+        WCT, aWCT, _, _, _ = po.wct(y1[b], y2[b], DT, dj=1 / 8, s0=2 * DT, J=65, sig=False, normalize=False)
+        W1 = po.cwt(y1[b], DT, 1 / 8, 2 * DT, 65)[0]
+        W2 = po.cwt(y2[b], DT, 1 / 8, 2 * DT, 65)[0]
+        ref12 = W1 * W2.conj()
+        for got in (w12[b], w12_g[b]):
+            assert np.abs(got - ref12).max() <= 1e-4 * np.abs(ref12).max()
+        for got in (wct[b], wct_g[b]):
+            assert np.abs(got - WCT).max() <= 2e-3 and np.abs(got - WCT).mean() <= 1e-4
+    assert np.abs(wct - wct_g).max() <= 2e-3
+
+
+def test_mc_cfg5_shape_fast_vs_generic_vs_oracle(shim):
+    """cfg5 / cfg3 Monte Carlo shape (J=65, dj=1/8 -> 3351 samples, FFT 4096), injected surrogates."""
+    dj, s0, J = 1 / 8, 2 * DT, 65
+    N, maxscale = shim.wct_mc_geometry(DT, dj, s0, J)
+    assert (N, maxscale) == (3351, 65)
+    rng = np.random.default_rng(77)
+    mc = 3
+    sur = np.stack([np.stack([po.rednoise(N, 0.989, 1, rng), po.rednoise(N, 0.966, 1, rng)]) for _ in range(mc)])
+    _, hist_ref = po.wct_significance(0.989, 0.966, DT, dj, s0, J, mc_count=mc, surrogates=sur, return_hist=True)
+    fast = shim.wct_mc_hist(0.989, 0.966, DT, dj, s0, J, mc_count=mc, surrogates=sur, f64=False)
+    gen = shim.wct_mc_hist(0.989, 0.966, DT, dj, s0, J, mc_count=mc, surrogates=sur, f64=False, generic_only=True)
+    f64 = shim.wct_mc_hist(0.989, 0.966, DT, dj, s0, J, mc_count=mc, surrogates=sur, f64=True)
+    assert fast.sum() == gen.sum() == f64.sum() == hist_ref.sum()
+    assert np.abs(f64.astype(np.int64) - hist_ref).sum() <= 6
+    cref = hist_ref.cumsum(axis=1) / np.maximum(hist_ref.sum(axis=1, keepdims=True), 1)
+    for h in (fast, gen):
+        c = h.cumsum(axis=1) / np.maximum(h.sum(axis=1, keepdims=True), 1)
+        assert np.abs(c - cref).max() <= 2e-3

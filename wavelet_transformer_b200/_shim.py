@@ -193,7 +193,7 @@ def cwt_power_device(x_ptr, batch, n0, dt, dj, s0, J, f0, power_ptr, *, nfft=Non
 
 # ---------------------------------------------------------------- XWT / WCT
 def xwt_wct(y1, y2, dt, dj, s0, J, f0=6.0, *, nfft=None, f64=None, want_wct=True, want_phase=True,
-            want_w12=False):
+            want_w12=False, generic_only=False):
     """Batched cross-wavelet / coherence of already-normalised host series.
     Returns (wct, phase, w12), each [batch, S, n0] or None."""
     f64 = _resolve_f64(f64)
@@ -209,7 +209,8 @@ def xwt_wct(y1, y2, dt, dj, s0, J, f0=6.0, *, nfft=None, f64=None, want_wct=True
     wct = np.empty((batch, S, n0), dtype=rt) if want_wct else None
     phase = np.empty((batch, S, n0), dtype=rt) if want_phase else None
     w12 = np.empty((batch, S, n0), dtype=np.complex128 if f64 else np.complex64) if want_w12 else None
-    _check(lib().wtb_xwt_wct(_ptr(a), _ptr(b), batch, n0, nfft, dt, dj, s0, int(J), f0, F64 if f64 else 0,
+    flags = (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0)
+    _check(lib().wtb_xwt_wct(_ptr(a), _ptr(b), batch, n0, nfft, dt, dj, s0, int(J), f0, flags,
                              _ptr(wct), _ptr(phase), _ptr(w12), None), "wtb_xwt_wct")
     if np.ndim(y1) == 1:
         wct, phase, w12 = (None if v is None else v[0] for v in (wct, phase, w12))
@@ -225,7 +226,7 @@ def wct_mc_geometry(dt, dj, s0, J, f0=6.0):
 
 
 def wct_mc_hist(a1, a2, dt, dj, s0, J, f0=6.0, *, mc_first=0, mc_count=300, seed=0, surrogates=None,
-                f64=None, white=False, hist=None):
+                f64=None, white=False, hist=None, generic_only=False):
     """Per-scale coherence histogram [S, 1000] (uint64) of `mc_count` realisations.
     `surrogates` ([mc_count, 2, nsurr] host array) switches to injected-noise mode."""
     f64 = _resolve_f64(f64)
@@ -238,7 +239,7 @@ def wct_mc_hist(a1, a2, dt, dj, s0, J, f0=6.0, *, mc_first=0, mc_count=300, seed
         sur = np.ascontiguousarray(surrogates, dtype=_dtype(f64))
         if sur.shape != (mc_count, 2, nsurr):
             raise ValueError(f"surrogates must have shape ({mc_count}, 2, {nsurr}), got {sur.shape}")
-    flags = (F64 if f64 else 0) | (NOISE_WHITE if white else 0)
+    flags = (F64 if f64 else 0) | (NOISE_WHITE if white else 0) | (GENERIC_ONLY if generic_only else 0)
     _check(lib().wtb_wct_mc_hist(a1, a2, dt, dj, s0, int(J), f0, int(mc_first), int(mc_count),
                                  C.c_uint64(int(seed)), _ptr(sur), flags, _ptr(hist), None), "wtb_wct_mc_hist")
     return hist

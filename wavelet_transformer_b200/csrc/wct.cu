@@ -14,7 +14,14 @@
 // smooth(|W1|^2) in its real part and smooth(|W2|^2) in its imaginary part.
 #include "spectral.cuh"
 
+#include <type_traits>
+
 namespace wtb {
+
+// wct_fast.cu: FP32 nfft=4096 register-FFT row kernel; returns 1 when not applicable
+int wct_rows_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax,
+                      double f0, void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_tsm,
+                      float *d_phase, float2 *d_w12, bool smooth, cudaStream_t st);
 
 template <typename T> struct vec4_of;
 template <> struct vec4_of<float> { using type = float4; };
@@ -95,6 +102,9 @@ __global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
     tsm[obase + t] = o;
   }
 }
+
+// set per call from WTB_GENERIC_ONLY (testing the generic kernels at the fast path's shapes)
+static thread_local bool g_force_generic = false;
 
 constexpr int kMaxWin = 64;
 struct ScaleWin {
@@ -177,8 +187,10 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   const size_t b_xh = al(sizeof(cplx<T>) * (size_t)pairs * 2 * N);
   const size_t b_ts = smooth ? al(sizeof(vec4<T>) * (size_t)pairs * S * n0) : 0;
   void *scratch = nullptr;
-  WTB_TRY(arena_reserve(b_sc + 2 * b_rng + b_xh + b_ts, &scratch));
+  const size_t b_rows = al(32 * (size_t)S);
+  WTB_TRY(arena_reserve(b_sc + 2 * b_rng + b_rows + b_xh + b_ts, &scratch));
   char *p = (char *)scratch;
+  void *d_rows_scratch = p; p += b_rows;
   double *d_scales = (double *)p; p += b_sc;
   int *d_tlo = (int *)p; p += b_rng;
   int *d_thi = (int *)p; p += b_rng;
@@ -196,9 +208,18 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   WTB_REQUIRE(pairs * S < (1LL << 31) && pairs * 2 < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
   k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
   WTB_LAUNCH_CHECK();
-  k_wct_rows<T><<<(unsigned)(pairs * S), threads, smem_rows, st>>>(
-      d_xhat, n0, N, log2N, S, d_scales, dt, f0, tw, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
-  WTB_LAUNCH_CHECK();
+  int fast_rc = 1;
+  if constexpr (std::is_same<T, float>::value) {
+    if (!g_force_generic)
+      fast_rc = wct_rows_fast_try((const float2 *)d_xhat, pairs, n0, N, dt, ax, f0, d_rows_scratch, b_rows,
+                                  (float4 *)d_tsm, (float *)d_phase, (float2 *)d_w12, smooth, st);
+    if (fast_rc < 0) return fast_rc;
+  }
+  if (fast_rc == 1) {
+    k_wct_rows<T><<<(unsigned)(pairs * S), threads, smem_rows, st>>>(
+        d_xhat, n0, N, log2N, S, d_scales, dt, f0, tw, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
+    WTB_LAUNCH_CHECK();
+  }
   if (smooth) {
     const int64_t cols = pairs * n0;
     const unsigned blocks = (unsigned)((cols + 255) / 256);
@@ -352,6 +373,7 @@ extern "C" int wtb_xwt_wct(const void *y1, const void *y2, int64_t batch, int n0
   WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));
   if (batch == 0) return WTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  g_force_generic = flags & WTB_GENERIC_ONLY;
   if (flags & WTB_F64)
     return xwt_wct_entry<double>(y1, y2, batch, n0, nfft, dt, dj, ax, f0, flags, wct_out, phase_out, w12_out, st);
   return xwt_wct_entry<float>(y1, y2, batch, n0, nfft, dt, dj, ax, f0, flags, wct_out, phase_out, w12_out, st);
@@ -370,6 +392,7 @@ extern "C" int wtb_wct_mc_hist(double a1, double a2, double dt, double dj, doubl
   WTB_TRY(resolve_axes(nsurr, dt, dj, s0, J, f0, &ax));
   if (mc_count == 0) return WTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  g_force_generic = flags & WTB_GENERIC_ONLY;
   if (flags & WTB_F64)
     return mc_hist_entry<double>(a1, a2, dt, dj, ax, f0, nsurr, maxscale, mc_first, mc_count, seed,
                                  surrogates, flags, hist, st);

@@ -1,0 +1,258 @@
+// FP32 fast path of the WCT row kernel for nfft = 4096 (BASELINE cfg5 and the Monte
+// Carlo inside cfg3: surrogates of 3351 samples padded to 4096).
+//
+// One CTA of 256 threads owns one (pair, scale) row.  A 4096-point transform is three
+// radix-16 passes; every thread keeps its 16 points in registers (fft16_gen.cuh,
+// Linzer-Feig FMA butterflies, literal twiddles) and the CTA exchanges data through a
+// padded shared-memory buffer between passes (Stockham index maps, in place).
+//
+// The three transform rounds of a row are chained through REGISTERS: pass 3 of a round
+// leaves thread j with elements j + 256 r', which are exactly the inputs of pass 1 of
+// the next round, so the pointwise steps (cross spectrum / windowing, Gaussian filter)
+// never touch shared or global memory:
+//   round 1  W1, W2 = IFFT(X^ * daughter_s)            (bins >= 2048 skipped, pass 1 pruned)
+//            P = (|W1|^2 + i |W2|^2)/s,  C = W1 conj(W2)/s,  zero for t >= n0
+//   round 2  P^, C^ = FFT(P), FFT(C)
+//            multiply by exp(-0.5 (s/dt)^2 k^2) / N
+//   round 3  T = IFFT(.)  ->  tsm[pair, s, t] = (T1, T2, Re T12, Im T12)
+// Both fields (two independent FFTs) move through each pass together.
+#include "common.cuh"
+#include "fft16_gen.cuh"
+
+namespace wtb {
+
+namespace {
+
+using fft16::br4;
+
+constexpr int kN = 4096;
+constexpr int kThreads = 256;
+constexpr int kBuf = kN + kN / 16;   // padded: index i lives at i + (i >> 4)
+
+struct WRow {
+  float a;        // (s/dt) * 2*pi/N : s*w_k = a*k
+  float lognorm;  // log2( sqrt(2*pi*s/dt) * pi^-1/4 / N )
+  float gcoef;    // -0.5 * log2(e) * a^2 : Gaussian exponent per squared bin index
+  float inv_s;    // 1 / scale
+  int R1;         // number of 256-bin blocks with daughter support (1..8)
+  int L1;         // ceil(log2(R1))
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmulcf(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
+
+// Passes 2 and 3 of a 4096-point transform for two fields at once.  On entry the
+// pass-1 outputs are in registers (natural order v[r']); on exit v[r'] holds element
+// j + 256 r' of the transform.  CONJ selects the forward sign.
+template <bool CONJ>
+__device__ __forceinline__ void passes23(float2 (&a)[16], float2 (&b)[16], float2 *U, float2 *V,
+                                         const float2 *__restrict__ tw2s, const float2 *__restrict__ tw3,
+                                         int j) {
+  const int k2 = j & 15;
+  // ---- exchange 1: pass-1 output index 16 j + r'
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    U[pad(16 * j + r)] = a[r];
+    V[pad(16 * j + r)] = b[r];
+  }
+  __syncthreads();
+  float2 c[16], d[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    float2 w = tw2s[r * 16 + k2];
+    if (CONJ) w.y = -w.y;
+    c[br4(r)] = cmulf(U[pad(j + 256 * r)], w);
+    d[br4(r)] = cmulf(V[pad(j + 256 * r)], w);
+  }
+  __syncthreads();
+  if (CONJ) { fft16::dit16_fwd(c); fft16::dit16_fwd(d); }
+  else { fft16::dit16_inv(c, 4); fft16::dit16_inv(d, 4); }
+  // ---- exchange 2: pass-2 output index (j - k2) * 16 + k2 + 16 r'
+  const int j0 = ((j - k2) << 4) + k2;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    U[pad(j0 + 16 * r)] = c[r];
+    V[pad(j0 + 16 * r)] = d[r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    float2 w = __ldg(&tw3[r * 256 + j]);
+    if (CONJ) w.y = -w.y;
+    a[br4(r)] = cmulf(U[pad(j + 256 * r)], w);
+    b[br4(r)] = cmulf(V[pad(j + 256 * r)], w);
+  }
+  __syncthreads();   // buffers are free again once every thread has loaded
+  if (CONJ) { fft16::dit16_fwd(a); fft16::dit16_fwd(b); }
+  else { fft16::dit16_inv(a, 4); fft16::dit16_inv(b, 4); }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_wct_rows_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__restrict__ rows,
+                const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
+                float4 *__restrict__ tsm, float *__restrict__ phase, float2 *__restrict__ w12,
+                int smooth) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *U = reinterpret_cast<float2 *>(smem_raw);
+  float2 *V = U + kBuf;
+  float2 *tw2s = V + kBuf;
+  const int j = threadIdx.x;
+  tw2s[j] = tw2[j];
+  const int64_t pair = blockIdx.x / S;
+  const int s = blockIdx.x % S;
+  const WRow rp = rows[s];
+  const float2 *x1 = xhat + (pair * 2) * (int64_t)kN;
+  const float2 *x2 = x1 + kN;
+  float2 a[16], b[16];
+
+  // ---- round 1, pass 1: Y[j + 256 r] for r < R1 (bins beyond the daughter's support are zero)
+  {
+    const float zl = fmaf(rp.a, (float)j, -f0);
+    const float a256 = rp.a * 256.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < rp.R1) {
+        const float z = fmaf(a256, (float)r, zl);
+        const float dgt = ex2(fmaf(z * z, -0.72134752044f, rp.lognorm));
+        const float2 p = __ldg(&x1[j + 256 * r]), q = __ldg(&x2[j + 256 * r]);
+        a[br4(r)] = make_float2(p.x * dgt, p.y * dgt);
+        b[br4(r)] = make_float2(q.x * dgt, q.y * dgt);
+      }
+    }
+    fft16::dit16_inv(a, rp.L1);
+    fft16::dit16_inv(b, rp.L1);
+  }
+  __syncthreads();   // tw2s visible
+  passes23<false>(a, b, U, V, tw2s, tw3, j);
+
+  // ---- pointwise: cross spectrum, window to n0, 1/s; outputs of the unsmoothed spectra
+  const int64_t obase = (pair * S + s) * (int64_t)n0;
+  float2 pq[16], cq[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int t = j + 256 * r;
+    float2 p = make_float2(0.0f, 0.0f), c = p;
+    if (t < n0) {
+      const float2 x = cmulcf(a[r], b[r]);
+      if (w12) w12[obase + t] = x;
+      if (phase) phase[obase + t] = atan2f(x.y, x.x);
+      p = make_float2(fmaf(a[r].x, a[r].x, a[r].y * a[r].y) * rp.inv_s,
+                      fmaf(b[r].x, b[r].x, b[r].y * b[r].y) * rp.inv_s);
+      c = make_float2(x.x * rp.inv_s, x.y * rp.inv_s);
+    }
+    pq[br4(r)] = p;
+    cq[br4(r)] = c;
+  }
+  if (!smooth) return;
+
+  // ---- round 2: forward transforms of P and C
+  fft16::dit16_fwd(pq);
+  fft16::dit16_fwd(cq);
+  passes23<true>(pq, cq, U, V, tw2s, tw3, j);
+
+  // ---- Gaussian filter in the Fourier domain (bin = j + 256 r), with the 1/N of the inverse
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int bin = j + 256 * r;
+    const float kk = (float)(bin < kN / 2 ? bin : bin - kN);
+    const float g = ex2(fmaf(rp.gcoef, kk * kk, -12.0f));
+    a[br4(r)] = make_float2(pq[r].x * g, pq[r].y * g);
+    b[br4(r)] = make_float2(cq[r].x * g, cq[r].y * g);
+  }
+
+  // ---- round 3: inverse transforms
+  fft16::dit16_inv(a, 4);
+  fft16::dit16_inv(b, 4);
+  passes23<false>(a, b, U, V, tw2s, tw3, j);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int t = j + 256 * r;
+    if (t < n0) tsm[obase + t] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
+  }
+}
+
+struct Tables {
+  float2 *tw2 = nullptr;   // [16][16]  exp(+2*pi*i*r*k/256)
+  float2 *tw3 = nullptr;   // [16][256] exp(+2*pi*i*r*j/4096)
+  int device = -1;
+};
+std::mutex g_tab_mu;
+Tables g_tab;
+
+int ensure_tables(const float2 **tw2, const float2 **tw3) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  int dev = 0;
+  WTB_CUDA(cudaGetDevice(&dev));
+  if (g_tab.device != dev) {
+    std::vector<float2> h2(256), h3(4096);
+    for (int r = 0; r < 16; ++r) {
+      for (int k = 0; k < 16; ++k) {
+        const long double ang = 2.0L * 3.141592653589793238462643383279502884L * r * k / 256.0L;
+        h2[r * 16 + k] = make_float2((float)cosl(ang), (float)sinl(ang));
+      }
+      for (int jj = 0; jj < 256; ++jj) {
+        const long double ang = 2.0L * 3.141592653589793238462643383279502884L * r * jj / 4096.0L;
+        h3[r * 256 + jj] = make_float2((float)cosl(ang), (float)sinl(ang));
+      }
+    }
+    float2 *d2 = nullptr, *d3 = nullptr;
+    WTB_CUDA(cudaMalloc(&d2, sizeof(float2) * 256));
+    WTB_CUDA(cudaMalloc(&d3, sizeof(float2) * 4096));
+    WTB_CUDA(cudaMemcpy(d2, h2.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
+    WTB_CUDA(cudaMemcpy(d3, h3.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice));
+    g_tab.tw2 = d2;   // kept for the life of the process (tiny)
+    g_tab.tw3 = d3;
+    g_tab.device = dev;
+  }
+  *tw2 = g_tab.tw2;
+  *tw3 = g_tab.tw3;
+  return WTB_OK;
+}
+
+}  // namespace
+
+// d_rows: device scratch for S WRow entries (caller's arena).  Returns 1 when the shape
+// is not covered by the fast path.
+int wct_rows_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax,
+                      double f0, void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_tsm,
+                      float *d_phase, float2 *d_w12, bool smooth, cudaStream_t st) {
+  const int S = ax.J + 1;
+  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes) return 1;
+  std::vector<WRow> rows(S);
+  for (int s = 0; s < S; ++s) {
+    const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
+    int khi = (int)std::floor((f0 + 5.3) / a);          // daughter < 8e-7 of its peak beyond
+    if (khi > kN / 2 - 1) khi = kN / 2 - 1;
+    if (khi < 1) khi = 1;
+    WRow &r = rows[s];
+    r.a = (float)a;
+    r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / kN);
+    r.gcoef = (float)(-0.5 * 1.4426950408889634 * a * a);
+    r.inv_s = (float)(1.0 / ax.scales[s]);
+    r.L1 = ilog2(khi / 256 + 1);
+    r.R1 = 1 << r.L1;               // whole power of two: every input the pruned DFT reads is set
+  }
+  const float2 *tw2 = nullptr, *tw3 = nullptr;
+  WTB_TRY(ensure_tables(&tw2, &tw3));
+  WRow *d_rows = (WRow *)d_rows_scratch;
+  WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WRow) * S, cudaMemcpyHostToDevice, st));
+  const size_t smem = sizeof(float2) * (2 * kBuf + 256);
+  WTB_CUDA(cudaFuncSetAttribute(k_wct_rows_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WTB_REQUIRE(pairs * S < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+  k_wct_rows_4096<<<(unsigned)(pairs * S), kThreads, smem, st>>>(d_xhat, n0, S, d_rows, tw2, tw3, (float)f0,
+                                                                d_tsm, d_phase, d_w12, smooth ? 1 : 0);
+  WTB_LAUNCH_CHECK();
+  return WTB_OK;
+}
+
+}  // namespace wtb

@@ -13,15 +13,18 @@
 // The Gaussian filter is real and even, so filtering the packed field P gives
 // smooth(|W1|^2) in its real part and smooth(|W2|^2) in its imaginary part.
 #include "spectral.cuh"
+#include "wct_common.cuh"
 
 #include <type_traits>
 
 namespace wtb {
 
-// wct_fast.cu: FP32 nfft=4096 register-FFT row kernel; returns 1 when not applicable
-int wct_rows_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax,
-                      double f0, void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_tsm,
-                      float *d_phase, float2 *d_w12, bool smooth, cudaStream_t st);
+// wct_fast.cu: FP32 nfft=4096 register-FFT pipeline (spectra kernel + coherence kernel);
+// returns 1 when the shape is not covered.  d_spec: [pairs, S, 4096] float4 scratch.
+int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax, double f0,
+                 void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_spec, const ScaleWin &win,
+                 float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
+                 const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st);
 
 template <typename T> struct vec4_of;
 template <> struct vec4_of<float> { using type = float4; };
@@ -106,13 +109,6 @@ __global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
 // set per call from WTB_GENERIC_ONLY (testing the generic kernels at the fast path's shapes)
 static thread_local bool g_force_generic = false;
 
-constexpr int kMaxWin = 64;
-struct ScaleWin {
-  int K;          // taps
-  int up;         // (K-1)/2: out[i] = sum_k win[k] * T[i + up - k]
-  double w[kMaxWin];
-};
-
 // One thread = one (pair, t) column; walks the scales.  MODE 0: write WCT plane;
 // MODE 1: add to the per-scale histogram for t inside [tlo[s], thi[s]] and s < maxscale.
 template <typename T, int MODE>
@@ -185,7 +181,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   const size_t b_sc = al(sizeof(double) * S);
   const size_t b_rng = al(sizeof(int) * S);
   const size_t b_xh = al(sizeof(cplx<T>) * (size_t)pairs * 2 * N);
-  const size_t b_ts = smooth ? al(sizeof(vec4<T>) * (size_t)pairs * S * n0) : 0;
+  const size_t b_ts = smooth ? al(sizeof(vec4<T>) * (size_t)pairs * S * N) : 0;  // N >= n0: also fits the fast path's spectra
   void *scratch = nullptr;
   const size_t b_rows = al(32 * (size_t)S);
   WTB_TRY(arena_reserve(b_sc + 2 * b_rng + b_rows + b_xh + b_ts, &scratch));
@@ -211,30 +207,31 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   int fast_rc = 1;
   if constexpr (std::is_same<T, float>::value) {
     if (!g_force_generic)
-      fast_rc = wct_rows_fast_try((const float2 *)d_xhat, pairs, n0, N, dt, ax, f0, d_rows_scratch, b_rows,
-                                  (float4 *)d_tsm, (float *)d_phase, (float2 *)d_w12, smooth, st);
+      fast_rc = wct_fast_try((const float2 *)d_xhat, pairs, n0, N, dt, ax, f0, d_rows_scratch, b_rows,
+                             (float4 *)d_tsm, win, (float *)d_wct, (float *)d_phase, (float2 *)d_w12, d_hist,
+                             d_tlo, d_thi, maxscale, st);
     if (fast_rc < 0) return fast_rc;
   }
   if (fast_rc == 1) {
     k_wct_rows<T><<<(unsigned)(pairs * S), threads, smem_rows, st>>>(
         d_xhat, n0, N, log2N, S, d_scales, dt, f0, tw, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
     WTB_LAUNCH_CHECK();
-  }
-  if (smooth) {
-    const int64_t cols = pairs * n0;
-    const unsigned blocks = (unsigned)((cols + 255) / 256);
-    if (d_hist)
-      k_wct_scale<T, 1><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, nullptr, d_hist, d_tlo, d_thi, maxscale);
-    else
-      k_wct_scale<T, 0><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, d_wct, nullptr, nullptr, nullptr, 0);
-    WTB_LAUNCH_CHECK();
+    if (smooth) {
+      const int64_t cols = pairs * n0;
+      const unsigned blocks = (unsigned)((cols + 255) / 256);
+      if (d_hist)
+        k_wct_scale<T, 1><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, nullptr, d_hist, d_tlo, d_thi, maxscale);
+      else
+        k_wct_scale<T, 0><<<blocks, 256, 0, st>>>(d_tsm, pairs, n0, S, win, d_wct, nullptr, nullptr, nullptr, 0);
+      WTB_LAUNCH_CHECK();
+    }
   }
   return WTB_OK;
 }
 
 // bytes of arena + staging one pair costs (for batching decisions)
 template <typename T> static size_t pair_bytes(int n0, int N, int S) {
-  return sizeof(cplx<T>) * 2 * (size_t)N + sizeof(vec4<T>) * (size_t)S * n0;
+  return sizeof(cplx<T>) * 2 * (size_t)N + sizeof(vec4<T>) * (size_t)S * N;
 }
 
 template <typename T>

@@ -13,10 +13,15 @@
 //   round 1  W1, W2 = IFFT(X^ * daughter_s)            (bins >= 2048 skipped, pass 1 pruned)
 //            P = (|W1|^2 + i |W2|^2)/s,  C = W1 conj(W2)/s,  zero for t >= n0
 //   round 2  P^, C^ = FFT(P), FFT(C)
-//            multiply by exp(-0.5 (s/dt)^2 k^2) / N
-//   round 3  T = IFFT(.)  ->  tsm[pair, s, t] = (T1, T2, Re T12, Im T12)
+//            G_s[k] = exp(-0.5 (s/dt)^2 k^2) / N * (P^, C^)[k]   -> spectra scratch (kernel A ends)
+//   round 3  S_i = IFFT( sum_m w_m G_{i+m} )                        (kernel B)
+//            coherence |S12|^2 / (S1 S2) -> plane, or -> per-scale histogram
+// The scale-axis boxcar of Morlet.smooth is applied to the filtered SPECTRA (it is a
+// linear combination of rows, so it commutes with the inverse transform).  Only bins
+// where a row's Gaussian exceeds 1e-7 are stored / read, which makes the scratch traffic
+// a fraction of a time-domain plane and removes the separate scale-smoothing pass.
 // Both fields (two independent FFTs) move through each pass together.
-#include "common.cuh"
+#include "wct_common.cuh"
 #include "fft16_gen.cuh"
 
 namespace wtb {
@@ -34,8 +39,10 @@ struct WRow {
   float lognorm;  // log2( sqrt(2*pi*s/dt) * pi^-1/4 / N )
   float gcoef;    // -0.5 * log2(e) * a^2 : Gaussian exponent per squared bin index
   float inv_s;    // 1 / scale
-  int R1;         // number of 256-bin blocks with daughter support (1..8)
-  int L1;         // ceil(log2(R1))
+  int R1;         // number of 256-bin blocks with daughter support (power of two, 1..8)
+  int L1;         // log2(R1)
+  float kc2;      // squared bin index beyond which the Gaussian filter is < 1e-7
+  int pad_;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -97,10 +104,11 @@ __device__ __forceinline__ void passes23(float2 (&a)[16], float2 (&b)[16], float
   else { fft16::dit16_inv(a, 4); fft16::dit16_inv(b, 4); }
 }
 
+// Kernel A: one CTA = one (pair, scale) row: rounds 1 and 2, filtered spectra out.
 __global__ void __launch_bounds__(kThreads, 2)
-k_wct_rows_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__restrict__ rows,
+k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__restrict__ rows,
                 const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
-                float4 *__restrict__ tsm, float *__restrict__ phase, float2 *__restrict__ w12,
+                float4 *__restrict__ spec, float *__restrict__ phase, float2 *__restrict__ w12,
                 int smooth) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *U = reinterpret_cast<float2 *>(smem_raw);
@@ -160,24 +168,101 @@ k_wct_rows_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
   fft16::dit16_fwd(cq);
   passes23<true>(pq, cq, U, V, tw2s, tw3, j);
 
-  // ---- Gaussian filter in the Fourier domain (bin = j + 256 r), with the 1/N of the inverse
+  // ---- Gaussian filter in the Fourier domain (bin = j + 256 r), with the 1/N of the inverse;
+  //      bins where the filter is negligible are neither stored nor ever read
+  float4 *srow = spec + (pair * S + s) * (int64_t)kN;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int bin = j + 256 * r;
     const float kk = (float)(bin < kN / 2 ? bin : bin - kN);
-    const float g = ex2(fmaf(rp.gcoef, kk * kk, -12.0f));
-    a[br4(r)] = make_float2(pq[r].x * g, pq[r].y * g);
-    b[br4(r)] = make_float2(cq[r].x * g, cq[r].y * g);
+    const float k2v = kk * kk;
+    if (k2v <= rp.kc2) {
+      const float g = ex2(fmaf(rp.gcoef, k2v, -12.0f));
+      srow[bin] = make_float4(pq[r].x * g, pq[r].y * g, cq[r].x * g, cq[r].y * g);
+    }
   }
+}
 
-  // ---- round 3: inverse transforms
+struct CohWin {
+  int K, up;
+  float w[kMaxWin];
+};
+
+// Kernel B: one CTA = one (pair, scale i): boxcar over the neighbouring rows' filtered
+// spectra, inverse transform, coherence -> plane (MODE 0) or per-scale histogram (MODE 1).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__restrict__ rows,
+               const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, CohWin win,
+               float *__restrict__ wct, unsigned long long *__restrict__ hist,
+               const int *__restrict__ tlo, const int *__restrict__ thi, int maxscale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *U = reinterpret_cast<float2 *>(smem_raw);
+  float2 *V = U + kBuf;
+  float2 *tw2s = V + kBuf;
+  unsigned int *shist = reinterpret_cast<unsigned int *>(tw2s + 256);   // MODE 1: 1000 bins
+  const int j = threadIdx.x;
+  const int64_t pair = blockIdx.x / S;
+  const int i = blockIdx.x % S;
+  if (MODE == 1 && i >= maxscale) return;
+  tw2s[j] = tw2[j];
+  if (MODE == 1)
+    for (int q = j; q < WTB_NBINS; q += kThreads) shist[q] = 0u;
+  float2 a[16], b[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) a[br4(r)] = b[br4(r)] = make_float2(0.0f, 0.0f);
+  const float4 *sp = spec + pair * (int64_t)S * kN;
+  for (int k = 0; k < win.K; ++k) {
+    const int row = i + win.up - k;
+    if (row < 0 || row >= S) continue;
+    const float kc2 = rows[row].kc2;
+    const float w = win.w[k];
+    const float4 *srow = sp + (int64_t)row * kN;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int bin = j + 256 * r;
+      const float kk = (float)(bin < kN / 2 ? bin : bin - kN);
+      if (kk * kk <= kc2) {
+        const float4 g = __ldg(&srow[bin]);
+        a[br4(r)].x = fmaf(w, g.x, a[br4(r)].x);
+        a[br4(r)].y = fmaf(w, g.y, a[br4(r)].y);
+        b[br4(r)].x = fmaf(w, g.z, b[br4(r)].x);
+        b[br4(r)].y = fmaf(w, g.w, b[br4(r)].y);
+      }
+    }
+  }
   fft16::dit16_inv(a, 4);
   fft16::dit16_inv(b, 4);
+  __syncthreads();   // tw2s / shist visible
   passes23<false>(a, b, U, V, tw2s, tw3, j);
+  // a = (S1, S2) packed as (re, im); b = S12
+  if (MODE == 0) {
+    float *orow = wct + (pair * S + i) * (int64_t)n0;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int t = j + 256 * r;
-    if (t < n0) tsm[obase + t] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
+    for (int r = 0; r < 16; ++r) {
+      const int t = j + 256 * r;
+      if (t < n0) orow[t] = fmaf(b[r].x, b[r].x, b[r].y * b[r].y) / (a[r].x * a[r].y);
+    }
+  } else {
+    const int lo = tlo[i], hi = thi[i];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int t = j + 256 * r;
+      if (t >= lo && t <= hi) {
+        const float r2 = fmaf(b[r].x, b[r].x, b[r].y * b[r].y) / (a[r].x * a[r].y);
+        if (r2 >= 0.0f) {   // NaN (0/0) is skipped
+          int bin = (int)floorf(r2 * (float)WTB_NBINS);
+          bin = min(bin, WTB_NBINS - 1);
+          atomicAdd(&shist[bin], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    unsigned long long *hrow = hist + (size_t)i * WTB_NBINS;
+    for (int q = j; q < WTB_NBINS; q += kThreads) {
+      const unsigned int c = shist[q];
+      if (c) atomicAdd(&hrow[q], (unsigned long long)c);
+    }
   }
 }
 
@@ -221,13 +306,15 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
 
 }  // namespace
 
-// d_rows: device scratch for S WRow entries (caller's arena).  Returns 1 when the shape
-// is not covered by the fast path.
-int wct_rows_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax,
-                      double f0, void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_tsm,
-                      float *d_phase, float2 *d_w12, bool smooth, cudaStream_t st) {
+// d_rows_scratch: device scratch for S WRow entries (caller's arena).  Returns 1 when the
+// shape is not covered by the fast path.
+int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax, double f0,
+                 void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_spec, const ScaleWin &win,
+                 float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
+                 const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st) {
   const int S = ax.J + 1;
   if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes) return 1;
+  const bool smooth = d_wct || d_hist;
   std::vector<WRow> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
@@ -241,16 +328,35 @@ int wct_rows_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double
     r.inv_s = (float)(1.0 / ax.scales[s]);
     r.L1 = ilog2(khi / 256 + 1);
     r.R1 = 1 << r.L1;               // whole power of two: every input the pruned DFT reads is set
+    const double kc = 5.68 / a;     // exp(-0.5 (a k)^2) < 1e-7 beyond
+    r.kc2 = (float)(kc * kc);
+    r.pad_ = 0;
   }
   const float2 *tw2 = nullptr, *tw3 = nullptr;
   WTB_TRY(ensure_tables(&tw2, &tw3));
   WRow *d_rows = (WRow *)d_rows_scratch;
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WRow) * S, cudaMemcpyHostToDevice, st));
-  const size_t smem = sizeof(float2) * (2 * kBuf + 256);
-  WTB_CUDA(cudaFuncSetAttribute(k_wct_rows_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem_a = sizeof(float2) * (2 * kBuf + 256);
+  const size_t smem_b = smem_a + sizeof(unsigned int) * WTB_NBINS;
+  WTB_CUDA(cudaFuncSetAttribute(k_wct_spec_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   WTB_REQUIRE(pairs * S < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
-  k_wct_rows_4096<<<(unsigned)(pairs * S), kThreads, smem, st>>>(d_xhat, n0, S, d_rows, tw2, tw3, (float)f0,
-                                                                d_tsm, d_phase, d_w12, smooth ? 1 : 0);
+  k_wct_spec_4096<<<(unsigned)(pairs * S), kThreads, smem_a, st>>>(d_xhat, n0, S, d_rows, tw2, tw3, (float)f0,
+                                                                  d_spec, d_phase, d_w12, smooth ? 1 : 0);
+  WTB_LAUNCH_CHECK();
+  if (!smooth) return WTB_OK;
+  CohWin cw;
+  cw.K = win.K;
+  cw.up = win.up;
+  for (int k = 0; k < win.K; ++k) cw.w[k] = (float)win.w[k];
+  if (d_hist) {
+    WTB_CUDA(cudaFuncSetAttribute(k_wct_coh_4096<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    k_wct_coh_4096<1><<<(unsigned)(pairs * S), kThreads, smem_b, st>>>(d_spec, n0, S, d_rows, tw2, tw3, cw, nullptr,
+                                                                      d_hist, d_tlo, d_thi, maxscale);
+  } else {
+    WTB_CUDA(cudaFuncSetAttribute(k_wct_coh_4096<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    k_wct_coh_4096<0><<<(unsigned)(pairs * S), kThreads, smem_b, st>>>(d_spec, n0, S, d_rows, tw2, tw3, cw, d_wct,
+                                                                      nullptr, nullptr, nullptr, 0);
+  }
   WTB_LAUNCH_CHECK();
   return WTB_OK;
 }

@@ -1,26 +1,27 @@
-// FP32 fast path of the WCT row kernel for nfft = 4096 (BASELINE cfg5 and the Monte
+// FP32 fast path of the coherence pipeline for nfft = 4096 (BASELINE cfg5 and the Monte
 // Carlo inside cfg3: surrogates of 3351 samples padded to 4096).
 //
-// One CTA of 256 threads owns one (pair, scale) row.  A 4096-point transform is three
-// radix-16 passes; every thread keeps its 16 points in registers (fft16_gen.cuh,
-// Linzer-Feig FMA butterflies, literal twiddles) and the CTA exchanges data through a
-// padded shared-memory buffer between passes (Stockham index maps, in place).
+// One CTA of 256 threads owns one (pair, scale) row and carries the row's TWO fields
+// (two independent 4096-point FFTs) through every pass together: twiddles and index
+// arithmetic are shared, and the shared-memory exchanges move both fields with one
+// 128-bit access.  A 4096-point transform is three radix-16 passes; every thread keeps
+// its 2 x 16 points in registers (fft16_gen.cuh: Linzer-Feig FMA butterflies, literal
+// twiddles); passes exchange data through one padded float4 buffer (Stockham index
+// maps, in place).  Forward transforms run the same inverse code on conjugated data, so
+// one pass body (one copy of the code, instruction-cache resident) serves every round.
 //
-// The three transform rounds of a row are chained through REGISTERS: pass 3 of a round
-// leaves thread j with elements j + 256 r', which are exactly the inputs of pass 1 of
-// the next round, so the pointwise steps (cross spectrum / windowing, Gaussian filter)
-// never touch shared or global memory:
-//   round 1  W1, W2 = IFFT(X^ * daughter_s)            (bins >= 2048 skipped, pass 1 pruned)
-//            P = (|W1|^2 + i |W2|^2)/s,  C = W1 conj(W2)/s,  zero for t >= n0
-//   round 2  P^, C^ = FFT(P), FFT(C)
-//            G_s[k] = exp(-0.5 (s/dt)^2 k^2) / N * (P^, C^)[k]   -> spectra scratch (kernel A ends)
-//   round 3  S_i = IFFT( sum_m w_m G_{i+m} )                        (kernel B)
-//            coherence |S12|^2 / (S1 S2) -> plane, or -> per-scale histogram
-// The scale-axis boxcar of Morlet.smooth is applied to the filtered SPECTRA (it is a
-// linear combination of rows, so it commutes with the inverse transform).  Only bins
-// where a row's Gaussian exceeds 1e-7 are stored / read, which makes the scratch traffic
-// a fraction of a time-domain plane and removes the separate scale-smoothing pass.
-// Both fields (two independent FFTs) move through each pass together.
+// The rounds of a row are chained through REGISTERS: pass 3 leaves thread j with
+// elements j + 256 r', which are exactly the inputs of pass 1 of the next round.
+//   kernel A  round 1  W1, W2 = IFFT(X^ * daughter_s)        (bins >= 2048 skipped, pass 1 pruned)
+//             pointwise P = (|W1|^2 + i |W2|^2)/s, C = W1 conj(W2)/s, zero for t >= n0
+//             round 2  P^, C^ = FFT(.)
+//             store    G_s[k] = exp(-0.5 (s/dt)^2 k^2)/N * (P^, C^)[k]  for bins with filter > 1e-7
+//   kernel B  load     sum_m w_m G_{i+m}[k]      scale boxcar of Morlet.smooth applied to spectra
+//             round 3  S1 + i S2, S12 = IFFT(.)
+//             |S12|^2 / (S1 S2) -> plane, or -> shared-memory histogram -> global
+// The boxcar is a linear combination of rows, so it commutes with the inverse transform;
+// applying it to the filtered spectra removes the time-domain plane round trip and the
+// separate scale-smoothing pass of the generic path.
 #include "wct_common.cuh"
 #include "fft16_gen.cuh"
 
@@ -32,7 +33,7 @@ using fft16::br4;
 
 constexpr int kN = 4096;
 constexpr int kThreads = 256;
-constexpr int kBuf = kN + kN / 16;   // padded: index i lives at i + (i >> 4)
+constexpr int kBuf = kN + kN / 16;     // padded: index i lives at i + (i >> 4)
 
 struct WRow {
   float a;        // (s/dt) * 2*pi/N : s*w_k = a*k
@@ -42,7 +43,12 @@ struct WRow {
   int R1;         // number of 256-bin blocks with daughter support (power of two, 1..8)
   int L1;         // log2(R1)
   float kc2;      // squared bin index beyond which the Gaussian filter is < 1e-7
-  int pad_;
+  int kc;         // floor(sqrt(kc2))
+};
+
+struct CohWin {
+  int K, up;
+  float w[kMaxWin];
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -53,77 +59,69 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
-__device__ __forceinline__ float2 cmulcf(float2 a, float2 b) {  // a * conj(b)
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
-}
 __device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 
-// Passes 2 and 3 of a 4096-point transform for two fields at once.  On entry the
-// pass-1 outputs are in registers (natural order v[r']); on exit v[r'] holds element
-// j + 256 r' of the transform.  CONJ selects the forward sign.
-template <bool CONJ>
-__device__ __forceinline__ void passes23(float2 (&a)[16], float2 (&b)[16], float2 *U, float2 *V,
-                                         const float2 *__restrict__ tw2s, const float2 *__restrict__ tw3,
-                                         int j) {
+// Inverse 4096-point transforms of both fields.  On entry a/b[br4(r)] hold input
+// j + 256 r (first 2^L of them non-zero); on exit a/b[r'] hold output j + 256 r'.
+// Contains 4 CTA barriers and ends with the buffer free.
+__device__ __forceinline__ void fft4096_inv2(float2 (&a)[16], float2 (&b)[16], int L, float4 *B,
+                                             const float2 *__restrict__ tw2s,
+                                             const float2 *__restrict__ tw3, int j) {
   const int k2 = j & 15;
-  // ---- exchange 1: pass-1 output index 16 j + r'
+  fft16::dit16_inv(a, L);
+  fft16::dit16_inv(b, L);
+  // exchange 1: pass-1 output index 16 j + r'
+#pragma unroll
+  for (int r = 0; r < 16; ++r) B[pad(16 * j + r)] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
+  __syncthreads();
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    U[pad(16 * j + r)] = a[r];
-    V[pad(16 * j + r)] = b[r];
+    const float4 q = B[pad(j + 256 * r)];
+    const float2 w = tw2s[r * 16 + k2];
+    a[br4(r)] = cmulf(make_float2(q.x, q.y), w);
+    b[br4(r)] = cmulf(make_float2(q.z, q.w), w);
   }
   __syncthreads();
-  float2 c[16], d[16];
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    float2 w = tw2s[r * 16 + k2];
-    if (CONJ) w.y = -w.y;
-    c[br4(r)] = cmulf(U[pad(j + 256 * r)], w);
-    d[br4(r)] = cmulf(V[pad(j + 256 * r)], w);
-  }
-  __syncthreads();
-  if (CONJ) { fft16::dit16_fwd(c); fft16::dit16_fwd(d); }
-  else { fft16::dit16_inv(c, 4); fft16::dit16_inv(d, 4); }
-  // ---- exchange 2: pass-2 output index (j - k2) * 16 + k2 + 16 r'
+  fft16::dit16_inv(a, 4);
+  fft16::dit16_inv(b, 4);
+  // exchange 2: pass-2 output index (j - k2) * 16 + k2 + 16 r'
   const int j0 = ((j - k2) << 4) + k2;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    U[pad(j0 + 16 * r)] = c[r];
-    V[pad(j0 + 16 * r)] = d[r];
-  }
+  for (int r = 0; r < 16; ++r) B[pad(j0 + 16 * r)] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    float2 w = __ldg(&tw3[r * 256 + j]);
-    if (CONJ) w.y = -w.y;
-    a[br4(r)] = cmulf(U[pad(j + 256 * r)], w);
-    b[br4(r)] = cmulf(V[pad(j + 256 * r)], w);
+    const float4 q = B[pad(j + 256 * r)];
+    const float2 w = __ldg(&tw3[r * 256 + j]);
+    a[br4(r)] = cmulf(make_float2(q.x, q.y), w);
+    b[br4(r)] = cmulf(make_float2(q.z, q.w), w);
   }
-  __syncthreads();   // buffers are free again once every thread has loaded
-  if (CONJ) { fft16::dit16_fwd(a); fft16::dit16_fwd(b); }
-  else { fft16::dit16_inv(a, 4); fft16::dit16_inv(b, 4); }
+  __syncthreads();   // buffer free again once every thread has loaded
+  fft16::dit16_inv(a, 4);
+  fft16::dit16_inv(b, 4);
 }
 
-// Kernel A: one CTA = one (pair, scale) row: rounds 1 and 2, filtered spectra out.
+// Kernel A: rounds 1 and 2 of one (pair, scale) row, filtered spectra out.
+// spec: [rows = pairs*S][4096] float4 = (P^.re, P^.im, C^.re, C^.im) * filter.
 __global__ void __launch_bounds__(kThreads, 2)
 k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__restrict__ rows,
                 const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
                 float4 *__restrict__ spec, float *__restrict__ phase, float2 *__restrict__ w12,
                 int smooth) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *U = reinterpret_cast<float2 *>(smem_raw);
-  float2 *V = U + kBuf;
-  float2 *tw2s = V + kBuf;
+  float4 *B = reinterpret_cast<float4 *>(smem_raw);                  // [kBuf]
+  float2 *tw2s = reinterpret_cast<float2 *>(B + kBuf);               // [256]
   const int j = threadIdx.x;
   tw2s[j] = tw2[j];
-  const int64_t pair = blockIdx.x / S;
-  const int s = blockIdx.x % S;
+  const int64_t row = blockIdx.x;
+  const int64_t pair = row / S;
+  const int s = (int)(row % S);
   const WRow rp = rows[s];
   const float2 *x1 = xhat + (pair * 2) * (int64_t)kN;
   const float2 *x2 = x1 + kN;
   float2 a[16], b[16];
 
-  // ---- round 1, pass 1: Y[j + 256 r] for r < R1 (bins beyond the daughter's support are zero)
+  // round 1, pass 1 inputs: Y[j + 256 r] for r < R1 (bins beyond the daughter's support are zero)
   {
     const float zl = fmaf(rp.a, (float)j, -f0);
     const float a256 = rp.a * 256.0f;
@@ -137,40 +135,41 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
         b[br4(r)] = make_float2(q.x * dgt, q.y * dgt);
       }
     }
-    fft16::dit16_inv(a, rp.L1);
-    fft16::dit16_inv(b, rp.L1);
   }
   __syncthreads();   // tw2s visible
-  passes23<false>(a, b, U, V, tw2s, tw3, j);
-
-  // ---- pointwise: cross spectrum, window to n0, 1/s; outputs of the unsmoothed spectra
-  const int64_t obase = (pair * S + s) * (int64_t)n0;
-  float2 pq[16], cq[16];
+  int L = rp.L1;
+#pragma unroll 1
+  for (int round = 0; round < 2; ++round) {
+    fft4096_inv2(a, b, L, B, tw2s, tw3, j);
+    if (round == 1) break;
+    // pointwise step; outputs are CONJUGATED so that round 2 (a forward transform) can
+    // reuse the inverse code: FFT(x) = conj(IFFT(conj(x)))
+    const int64_t obase = row * (int64_t)n0;
+    float2 na[16], nb[16];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int t = j + 256 * r;
-    float2 p = make_float2(0.0f, 0.0f), c = p;
-    if (t < n0) {
-      const float2 x = cmulcf(a[r], b[r]);
-      if (w12) w12[obase + t] = x;
-      if (phase) phase[obase + t] = atan2f(x.y, x.x);
-      p = make_float2(fmaf(a[r].x, a[r].x, a[r].y * a[r].y) * rp.inv_s,
-                      fmaf(b[r].x, b[r].x, b[r].y * b[r].y) * rp.inv_s);
-      c = make_float2(x.x * rp.inv_s, x.y * rp.inv_s);
+    for (int r = 0; r < 16; ++r) {
+      const int t = j + 256 * r;
+      float2 p = make_float2(0.0f, 0.0f), c = p;
+      if (t < n0) {
+        const float xr = fmaf(a[r].x, b[r].x, a[r].y * b[r].y);     // W1 conj(W2)
+        const float xi = fmaf(a[r].y, b[r].x, -a[r].x * b[r].y);
+        if (w12) w12[obase + t] = make_float2(xr, xi);
+        if (phase) phase[obase + t] = atan2f(xi, xr);
+        p = make_float2(fmaf(a[r].x, a[r].x, a[r].y * a[r].y) * rp.inv_s,
+                        -fmaf(b[r].x, b[r].x, b[r].y * b[r].y) * rp.inv_s);
+        c = make_float2(xr * rp.inv_s, -xi * rp.inv_s);
+      }
+      na[br4(r)] = p;
+      nb[br4(r)] = c;
     }
-    pq[br4(r)] = p;
-    cq[br4(r)] = c;
+    if (!smooth) return;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { a[r] = na[r]; b[r] = nb[r]; }
+    L = 4;
   }
-  if (!smooth) return;
-
-  // ---- round 2: forward transforms of P and C
-  fft16::dit16_fwd(pq);
-  fft16::dit16_fwd(cq);
-  passes23<true>(pq, cq, U, V, tw2s, tw3, j);
-
-  // ---- Gaussian filter in the Fourier domain (bin = j + 256 r), with the 1/N of the inverse;
-  //      bins where the filter is negligible are neither stored nor ever read
-  float4 *srow = spec + (pair * S + s) * (int64_t)kN;
+  // a, b = conj(FFT(field)); Gaussian filter in the Fourier domain with the 1/N of the
+  // inverse.  Bins where the filter is negligible are neither stored nor ever read.
+  float4 *srow = spec + row * (int64_t)kN;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int bin = j + 256 * r;
@@ -178,15 +177,10 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
     const float k2v = kk * kk;
     if (k2v <= rp.kc2) {
       const float g = ex2(fmaf(rp.gcoef, k2v, -12.0f));
-      srow[bin] = make_float4(pq[r].x * g, pq[r].y * g, cq[r].x * g, cq[r].y * g);
+      srow[bin] = make_float4(a[r].x * g, -a[r].y * g, b[r].x * g, -b[r].y * g);
     }
   }
 }
-
-struct CohWin {
-  int K, up;
-  float w[kMaxWin];
-};
 
 // Kernel B: one CTA = one (pair, scale i): boxcar over the neighbouring rows' filtered
 // spectra, inverse transform, coherence -> plane (MODE 0) or per-scale histogram (MODE 1).
@@ -197,13 +191,13 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
                float *__restrict__ wct, unsigned long long *__restrict__ hist,
                const int *__restrict__ tlo, const int *__restrict__ thi, int maxscale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *U = reinterpret_cast<float2 *>(smem_raw);
-  float2 *V = U + kBuf;
-  float2 *tw2s = V + kBuf;
+  float4 *B = reinterpret_cast<float4 *>(smem_raw);
+  float2 *tw2s = reinterpret_cast<float2 *>(B + kBuf);
   unsigned int *shist = reinterpret_cast<unsigned int *>(tw2s + 256);   // MODE 1: 1000 bins
   const int j = threadIdx.x;
-  const int64_t pair = blockIdx.x / S;
-  const int i = blockIdx.x % S;
+  const int64_t row = blockIdx.x;
+  const int64_t pair = row / S;
+  const int i = (int)(row % S);
   if (MODE == 1 && i >= maxscale) return;
   tw2s[j] = tw2[j];
   if (MODE == 1)
@@ -212,18 +206,20 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
 #pragma unroll
   for (int r = 0; r < 16; ++r) a[br4(r)] = b[br4(r)] = make_float2(0.0f, 0.0f);
   const float4 *sp = spec + pair * (int64_t)S * kN;
+#pragma unroll 1
   for (int k = 0; k < win.K; ++k) {
-    const int row = i + win.up - k;
-    if (row < 0 || row >= S) continue;
-    const float kc2 = rows[row].kc2;
+    const int rw = i + win.up - k;
+    if (rw < 0 || rw >= S) continue;
+    // bins j + 256 r inside the row's pass band: bin <= kc or bin >= N - kc
+    const int kc = rows[rw].kc;
+    const int r_lo = (kc - j) >> 8;                      // r <= r_lo   (negative: none)
+    const int r_hi = (kN - kc - j + 255) >> 8;           // r >= r_hi
     const float w = win.w[k];
-    const float4 *srow = sp + (int64_t)row * kN;
+    const float4 *srow = sp + (int64_t)rw * kN + j;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      const int bin = j + 256 * r;
-      const float kk = (float)(bin < kN / 2 ? bin : bin - kN);
-      if (kk * kk <= kc2) {
-        const float4 g = __ldg(&srow[bin]);
+      if (r <= r_lo || r >= r_hi) {
+        const float4 g = __ldg(&srow[256 * r]);
         a[br4(r)].x = fmaf(w, g.x, a[br4(r)].x);
         a[br4(r)].y = fmaf(w, g.y, a[br4(r)].y);
         b[br4(r)].x = fmaf(w, g.z, b[br4(r)].x);
@@ -231,13 +227,11 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
       }
     }
   }
-  fft16::dit16_inv(a, 4);
-  fft16::dit16_inv(b, 4);
   __syncthreads();   // tw2s / shist visible
-  passes23<false>(a, b, U, V, tw2s, tw3, j);
-  // a = (S1, S2) packed as (re, im); b = S12
+  fft4096_inv2(a, b, 4, B, tw2s, tw3, j);
+  // a = (S1, S2) carried as (re, im); b = S12
   if (MODE == 0) {
-    float *orow = wct + (pair * S + i) * (int64_t)n0;
+    float *orow = wct + row * (int64_t)n0;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int t = j + 256 * r;
@@ -280,13 +274,14 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
   WTB_CUDA(cudaGetDevice(&dev));
   if (g_tab.device != dev) {
     std::vector<float2> h2(256), h3(4096);
+    const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
     for (int r = 0; r < 16; ++r) {
       for (int k = 0; k < 16; ++k) {
-        const long double ang = 2.0L * 3.141592653589793238462643383279502884L * r * k / 256.0L;
+        const long double ang = two_pi * r * k / 256.0L;
         h2[r * 16 + k] = make_float2((float)cosl(ang), (float)sinl(ang));
       }
       for (int jj = 0; jj < 256; ++jj) {
-        const long double ang = 2.0L * 3.141592653589793238462643383279502884L * r * jj / 4096.0L;
+        const long double ang = two_pi * r * jj / 4096.0L;
         h3[r * 256 + jj] = make_float2((float)cosl(ang), (float)sinl(ang));
       }
     }
@@ -295,7 +290,7 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
     WTB_CUDA(cudaMalloc(&d3, sizeof(float2) * 4096));
     WTB_CUDA(cudaMemcpy(d2, h2.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
     WTB_CUDA(cudaMemcpy(d3, h3.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice));
-    g_tab.tw2 = d2;   // kept for the life of the process (tiny)
+    g_tab.tw2 = d2;   // kept for the life of the process (34 KB)
     g_tab.tw3 = d3;
     g_tab.device = dev;
   }
@@ -306,8 +301,8 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
 
 }  // namespace
 
-// d_rows_scratch: device scratch for S WRow entries (caller's arena).  Returns 1 when the
-// shape is not covered by the fast path.
+// d_rows_scratch: device scratch for S WRow entries (caller's arena); d_spec: scratch of
+// pairs*S*4096 float4-equivalents.  Returns 1 when the shape is not covered.
 int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax, double f0,
                  void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_spec, const ScaleWin &win,
                  float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
@@ -329,19 +324,22 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
     r.L1 = ilog2(khi / 256 + 1);
     r.R1 = 1 << r.L1;               // whole power of two: every input the pruned DFT reads is set
     const double kc = 5.68 / a;     // exp(-0.5 (a k)^2) < 1e-7 beyond
-    r.kc2 = (float)(kc * kc);
-    r.pad_ = 0;
+    r.kc = (int)std::floor(kc);
+    if (r.kc > kN / 2) r.kc = kN / 2;
+    r.kc2 = (float)r.kc * (float)r.kc;   // kernel A stores exactly the bins kernel B reads
   }
   const float2 *tw2 = nullptr, *tw3 = nullptr;
   WTB_TRY(ensure_tables(&tw2, &tw3));
   WRow *d_rows = (WRow *)d_rows_scratch;
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WRow) * S, cudaMemcpyHostToDevice, st));
-  const size_t smem_a = sizeof(float2) * (2 * kBuf + 256);
+  const size_t smem_a = sizeof(float4) * kBuf + sizeof(float2) * 256;
   const size_t smem_b = smem_a + sizeof(unsigned int) * WTB_NBINS;
+  const int64_t nrows = pairs * S;
+  WTB_REQUIRE(nrows < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+  float4 *spec = d_spec;
   WTB_CUDA(cudaFuncSetAttribute(k_wct_spec_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-  WTB_REQUIRE(pairs * S < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
-  k_wct_spec_4096<<<(unsigned)(pairs * S), kThreads, smem_a, st>>>(d_xhat, n0, S, d_rows, tw2, tw3, (float)f0,
-                                                                  d_spec, d_phase, d_w12, smooth ? 1 : 0);
+  k_wct_spec_4096<<<(unsigned)nrows, kThreads, smem_a, st>>>(d_xhat, n0, S, d_rows, tw2, tw3, (float)f0,
+                                                            spec, d_phase, d_w12, smooth ? 1 : 0);
   WTB_LAUNCH_CHECK();
   if (!smooth) return WTB_OK;
   CohWin cw;
@@ -350,12 +348,12 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
   for (int k = 0; k < win.K; ++k) cw.w[k] = (float)win.w[k];
   if (d_hist) {
     WTB_CUDA(cudaFuncSetAttribute(k_wct_coh_4096<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    k_wct_coh_4096<1><<<(unsigned)(pairs * S), kThreads, smem_b, st>>>(d_spec, n0, S, d_rows, tw2, tw3, cw, nullptr,
-                                                                      d_hist, d_tlo, d_thi, maxscale);
+    k_wct_coh_4096<1><<<(unsigned)nrows, kThreads, smem_b, st>>>(spec, n0, S, d_rows, tw2, tw3, cw, nullptr,
+                                                                d_hist, d_tlo, d_thi, maxscale);
   } else {
     WTB_CUDA(cudaFuncSetAttribute(k_wct_coh_4096<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    k_wct_coh_4096<0><<<(unsigned)(pairs * S), kThreads, smem_b, st>>>(d_spec, n0, S, d_rows, tw2, tw3, cw, d_wct,
-                                                                      nullptr, nullptr, nullptr, 0);
+    k_wct_coh_4096<0><<<(unsigned)nrows, kThreads, smem_b, st>>>(spec, n0, S, d_rows, tw2, tw3, cw, d_wct,
+                                                                nullptr, nullptr, nullptr, 0);
   }
   WTB_LAUNCH_CHECK();
   return WTB_OK;

@@ -56,54 +56,57 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
 __device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 
-// Inverse 4096-point transforms of both fields.  On entry a/b[br4(r)] hold input
-// j + 256 r (first 2^L of them non-zero); on exit a/b[r'] hold output j + 256 r'.
+using fft32::bc;
+using fft32::fma2;
+using fft32::mul2;
+
+// Registers: R[p] = (re of field 0, re of field 1), I[p] = (im of field 0, im of field 1):
+// both fields of the row ride in the two lanes of every FFMA2 / FADD2 / FMUL2.
+//
+// Inverse 4096-point transforms of both fields.  On entry R/I[br4(r)] hold input
+// j + 256 r (first 2^L of them non-zero); on exit R/I[r'] hold output j + 256 r'.
 // Contains 4 CTA barriers and ends with the buffer free.
-__device__ __forceinline__ void fft4096_inv2(float2 (&a)[16], float2 (&b)[16], int L, float4 *B,
+__device__ __forceinline__ void fft4096_inv2(float2 (&R)[16], float2 (&I)[16], int L, float4 *B,
                                              const float2 *__restrict__ tw2s,
                                              const float2 *__restrict__ tw3, int j) {
   const int k2 = j & 15;
-  fft16::dit16_inv(a, L);
-  fft16::dit16_inv(b, L);
+  fft16::dit16p_inv(R, I, L);
   // exchange 1: pass-1 output index 16 j + r'
 #pragma unroll
-  for (int r = 0; r < 16; ++r) B[pad(16 * j + r)] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
+  for (int r = 0; r < 16; ++r) B[pad(16 * j + r)] = make_float4(R[r].x, R[r].y, I[r].x, I[r].y);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const float4 q = B[pad(j + 256 * r)];
     const float2 w = tw2s[r * 16 + k2];
-    a[br4(r)] = cmulf(make_float2(q.x, q.y), w);
-    b[br4(r)] = cmulf(make_float2(q.z, q.w), w);
+    const float2 qr = make_float2(q.x, q.y), qi = make_float2(q.z, q.w);
+    R[br4(r)] = fma2(qi, bc(-w.y), mul2(qr, bc(w.x)));
+    I[br4(r)] = fma2(qr, bc(w.y), mul2(qi, bc(w.x)));
   }
   __syncthreads();
-  fft16::dit16_inv(a, 4);
-  fft16::dit16_inv(b, 4);
+  fft16::dit16p_inv(R, I, 4);
   // exchange 2: pass-2 output index (j - k2) * 16 + k2 + 16 r'
   const int j0 = ((j - k2) << 4) + k2;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) B[pad(j0 + 16 * r)] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
+  for (int r = 0; r < 16; ++r) B[pad(j0 + 16 * r)] = make_float4(R[r].x, R[r].y, I[r].x, I[r].y);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const float4 q = B[pad(j + 256 * r)];
     const float2 w = __ldg(&tw3[r * 256 + j]);
-    a[br4(r)] = cmulf(make_float2(q.x, q.y), w);
-    b[br4(r)] = cmulf(make_float2(q.z, q.w), w);
+    const float2 qr = make_float2(q.x, q.y), qi = make_float2(q.z, q.w);
+    R[br4(r)] = fma2(qi, bc(-w.y), mul2(qr, bc(w.x)));
+    I[br4(r)] = fma2(qr, bc(w.y), mul2(qi, bc(w.x)));
   }
   __syncthreads();   // buffer free again once every thread has loaded
-  fft16::dit16_inv(a, 4);
-  fft16::dit16_inv(b, 4);
+  fft16::dit16p_inv(R, I, 4);
 }
 
 // Kernel A: rounds 1 and 2 of one (pair, scale) row, filtered spectra out.
-// spec: [rows = pairs*S][4096] float4 = (P^.re, P^.im, C^.re, C^.im) * filter.
-__global__ void __launch_bounds__(kThreads, 2)
+// spec: [rows = pairs*S][4096] float4 = (P^.re, C^.re, P^.im, C^.im) * filter.
+__global__ void __launch_bounds__(kThreads, 3)
 k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__restrict__ rows,
                 const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
                 float4 *__restrict__ spec, float *__restrict__ phase, float2 *__restrict__ w12,
@@ -119,7 +122,7 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
   const WRow rp = rows[s];
   const float2 *x1 = xhat + (pair * 2) * (int64_t)kN;
   const float2 *x2 = x1 + kN;
-  float2 a[16], b[16];
+  float2 R[16], I[16];
 
   // round 1, pass 1 inputs: Y[j + 256 r] for r < R1 (bins beyond the daughter's support are zero)
   {
@@ -129,10 +132,10 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
     for (int r = 0; r < 8; ++r) {
       if (r < rp.R1) {
         const float z = fmaf(a256, (float)r, zl);
-        const float dgt = ex2(fmaf(z * z, -0.72134752044f, rp.lognorm));
+        const float2 dgt = bc(ex2(fmaf(z * z, -0.72134752044f, rp.lognorm)));
         const float2 p = __ldg(&x1[j + 256 * r]), q = __ldg(&x2[j + 256 * r]);
-        a[br4(r)] = make_float2(p.x * dgt, p.y * dgt);
-        b[br4(r)] = make_float2(q.x * dgt, q.y * dgt);
+        R[br4(r)] = mul2(make_float2(p.x, q.x), dgt);
+        I[br4(r)] = mul2(make_float2(p.y, q.y), dgt);
       }
     }
   }
@@ -140,34 +143,35 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
   int L = rp.L1;
 #pragma unroll 1
   for (int round = 0; round < 2; ++round) {
-    fft4096_inv2(a, b, L, B, tw2s, tw3, j);
+    fft4096_inv2(R, I, L, B, tw2s, tw3, j);
     if (round == 1) break;
-    // pointwise step; outputs are CONJUGATED so that round 2 (a forward transform) can
-    // reuse the inverse code: FFT(x) = conj(IFFT(conj(x)))
+    // pointwise step: lane 0 becomes P = (|W1|^2 + i |W2|^2)/s, lane 1 becomes
+    // C = W1 conj(W2)/s.  Both are CONJUGATED so that round 2 (a forward transform) can
+    // reuse the inverse code: FFT(x) = conj(IFFT(conj(x))).
     const int64_t obase = row * (int64_t)n0;
-    float2 na[16], nb[16];
+    float2 nR[16], nI[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int t = j + 256 * r;
-      float2 p = make_float2(0.0f, 0.0f), c = p;
+      float2 pr = make_float2(0.0f, 0.0f), pi = pr;
       if (t < n0) {
-        const float xr = fmaf(a[r].x, b[r].x, a[r].y * b[r].y);     // W1 conj(W2)
-        const float xi = fmaf(a[r].y, b[r].x, -a[r].x * b[r].y);
+        const float2 m2 = fma2(R[r], R[r], mul2(I[r], I[r]));          // (|W1|^2, |W2|^2)
+        const float xr = fmaf(R[r].x, R[r].y, I[r].x * I[r].y);        // W1 conj(W2)
+        const float xi = fmaf(I[r].x, R[r].y, -R[r].x * I[r].y);
         if (w12) w12[obase + t] = make_float2(xr, xi);
         if (phase) phase[obase + t] = atan2f(xi, xr);
-        p = make_float2(fmaf(a[r].x, a[r].x, a[r].y * a[r].y) * rp.inv_s,
-                        -fmaf(b[r].x, b[r].x, b[r].y * b[r].y) * rp.inv_s);
-        c = make_float2(xr * rp.inv_s, -xi * rp.inv_s);
+        pr = make_float2(m2.x * rp.inv_s, xr * rp.inv_s);
+        pi = make_float2(-m2.y * rp.inv_s, -xi * rp.inv_s);
       }
-      na[br4(r)] = p;
-      nb[br4(r)] = c;
+      nR[br4(r)] = pr;
+      nI[br4(r)] = pi;
     }
     if (!smooth) return;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) { a[r] = na[r]; b[r] = nb[r]; }
+    for (int r = 0; r < 16; ++r) { R[r] = nR[r]; I[r] = nI[r]; }
     L = 4;
   }
-  // a, b = conj(FFT(field)); Gaussian filter in the Fourier domain with the 1/N of the
+  // (R, I) = conj(FFT(field)); Gaussian filter in the Fourier domain with the 1/N of the
   // inverse.  Bins where the filter is negligible are neither stored nor ever read.
   float4 *srow = spec + row * (int64_t)kN;
 #pragma unroll
@@ -177,15 +181,59 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
     const float k2v = kk * kk;
     if (k2v <= rp.kc2) {
       const float g = ex2(fmaf(rp.gcoef, k2v, -12.0f));
-      srow[bin] = make_float4(a[r].x * g, -a[r].y * g, b[r].x * g, -b[r].y * g);
+      srow[bin] = make_float4(R[r].x * g, R[r].y * g, -I[r].x * g, -I[r].y * g);
     }
+  }
+}
+
+// Kernel C: scale-axis boxcar of Morlet.smooth applied to the filtered spectra, in place.
+// One thread owns one frequency bin of one pair and slides over the scales with a ring of
+// the last K input rows in shared memory (column-private, so in-place is safe): every
+// spectrum is read once and every smoothed spectrum written once.
+// H_i[bin] = sum_k w[k] * G_{i+up-k}[bin]; rows outside [0, S) and bins outside a row's
+// pass band count as zero.  Row i is written for bins inside the widest band of its window.
+__global__ void __launch_bounds__(kThreads)
+k_wct_boxcar_4096(float4 *__restrict__ spec, int S, const WRow *__restrict__ rows, CohWin win) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *ring = reinterpret_cast<float4 *>(smem_raw);     // [K][kThreads]
+  const int tid = threadIdx.x;
+  const int64_t pair = blockIdx.x >> 4;
+  const int bin = ((blockIdx.x & 15) << 8) + tid;
+  const int akk = bin < kN / 2 ? bin : kN - bin;
+  if (akk > rows[0].kc) return;                            // outside every row's pass band
+  float4 *col = spec + pair * (int64_t)S * kN + bin;
+  const int K = win.K, up = win.up;
+  const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int k = 0; k < K; ++k) ring[k * kThreads + tid] = zero;
+  int slot = 0;                                             // ring slot of input row s_in
+  for (int s_in = 0; s_in < S + up; ++s_in) {
+    float4 v = zero;
+    if (s_in < S && akk <= rows[s_in].kc) v = col[(int64_t)s_in * kN];
+    ring[slot * kThreads + tid] = v;
+    const int i = s_in - up;                                // output row completed by this input
+    if (i >= 0) {
+      const int first = i + up - (K - 1);                   // smallest-scale row of the window
+      if (akk <= rows[first < 0 ? 0 : first].kc) {
+        float4 acc = zero;
+        int sl = slot;                                      // k = 0 <-> row i + up = s_in
+        for (int k = 0; k < K; ++k) {
+          const float4 g = ring[sl * kThreads + tid];
+          const float w = win.w[k];
+          acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
+          acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+          sl = sl == 0 ? K - 1 : sl - 1;
+        }
+        col[(int64_t)i * kN] = acc;
+      }
+    }
+    slot = slot + 1 == K ? 0 : slot + 1;
   }
 }
 
 // Kernel B: one CTA = one (pair, scale i): boxcar over the neighbouring rows' filtered
 // spectra, inverse transform, coherence -> plane (MODE 0) or per-scale histogram (MODE 1).
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__restrict__ rows,
                const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, CohWin win,
                float *__restrict__ wct, unsigned long long *__restrict__ hist,
@@ -196,46 +244,34 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
   unsigned int *shist = reinterpret_cast<unsigned int *>(tw2s + 256);   // MODE 1: 1000 bins
   const int j = threadIdx.x;
   const int64_t row = blockIdx.x;
-  const int64_t pair = row / S;
   const int i = (int)(row % S);
   if (MODE == 1 && i >= maxscale) return;
   tw2s[j] = tw2[j];
   if (MODE == 1)
     for (int q = j; q < WTB_NBINS; q += kThreads) shist[q] = 0u;
-  float2 a[16], b[16];
+  // smoothed spectrum of this row (kernel C): bins inside the widest pass band of its window
+  const int first = i + win.up - (win.K - 1);
+  const int kc = rows[first < 0 ? 0 : first].kc;
+  const int r_lo = (kc - j) >> 8;                         // bins j + 256 r <= kc
+  const int r_hi = (kN - kc - j + 255) >> 8;              // bins j + 256 r >= N - kc
+  const float4 *srow = spec + row * (int64_t)kN + j;
+  float2 R[16], I[16];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) a[br4(r)] = b[br4(r)] = make_float2(0.0f, 0.0f);
-  const float4 *sp = spec + pair * (int64_t)S * kN;
-#pragma unroll 1
-  for (int k = 0; k < win.K; ++k) {
-    const int rw = i + win.up - k;
-    if (rw < 0 || rw >= S) continue;
-    // bins j + 256 r inside the row's pass band: bin <= kc or bin >= N - kc
-    const int kc = rows[rw].kc;
-    const int r_lo = (kc - j) >> 8;                      // r <= r_lo   (negative: none)
-    const int r_hi = (kN - kc - j + 255) >> 8;           // r >= r_hi
-    const float w = win.w[k];
-    const float4 *srow = sp + (int64_t)rw * kN + j;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      if (r <= r_lo || r >= r_hi) {
-        const float4 g = __ldg(&srow[256 * r]);
-        a[br4(r)].x = fmaf(w, g.x, a[br4(r)].x);
-        a[br4(r)].y = fmaf(w, g.y, a[br4(r)].y);
-        b[br4(r)].x = fmaf(w, g.z, b[br4(r)].x);
-        b[br4(r)].y = fmaf(w, g.w, b[br4(r)].y);
-      }
-    }
+  for (int r = 0; r < 16; ++r) {
+    float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (r <= r_lo || r >= r_hi) g = __ldg(srow + 256 * r);
+    R[br4(r)] = make_float2(g.x, g.y);
+    I[br4(r)] = make_float2(g.z, g.w);
   }
   __syncthreads();   // tw2s / shist visible
-  fft4096_inv2(a, b, 4, B, tw2s, tw3, j);
-  // a = (S1, S2) carried as (re, im); b = S12
+  fft4096_inv2(R, I, 4, B, tw2s, tw3, j);
+  // lane 0 = S1 + i S2 (two real fields), lane 1 = S12
   if (MODE == 0) {
     float *orow = wct + row * (int64_t)n0;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int t = j + 256 * r;
-      if (t < n0) orow[t] = fmaf(b[r].x, b[r].x, b[r].y * b[r].y) / (a[r].x * a[r].y);
+      if (t < n0) orow[t] = fmaf(R[r].y, R[r].y, I[r].y * I[r].y) / (R[r].x * I[r].x);
     }
   } else {
     const int lo = tlo[i], hi = thi[i];
@@ -243,7 +279,7 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
     for (int r = 0; r < 16; ++r) {
       const int t = j + 256 * r;
       if (t >= lo && t <= hi) {
-        const float r2 = fmaf(b[r].x, b[r].x, b[r].y * b[r].y) / (a[r].x * a[r].y);
+        const float r2 = fmaf(R[r].y, R[r].y, I[r].y * I[r].y) / (R[r].x * I[r].x);
         if (r2 >= 0.0f) {   // NaN (0/0) is skipped
           int bin = (int)floorf(r2 * (float)WTB_NBINS);
           bin = min(bin, WTB_NBINS - 1);
@@ -308,7 +344,7 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
                  float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
                  const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes) return 1;
+  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32) return 1;
   const bool smooth = d_wct || d_hist;
   std::vector<WRow> rows(S);
   for (int s = 0; s < S; ++s) {
@@ -346,6 +382,12 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
   cw.K = win.K;
   cw.up = win.up;
   for (int k = 0; k < win.K; ++k) cw.w[k] = (float)win.w[k];
+  {
+    const size_t smem_c = sizeof(float4) * (size_t)cw.K * kThreads;
+    WTB_CUDA(cudaFuncSetAttribute(k_wct_boxcar_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    k_wct_boxcar_4096<<<(unsigned)(pairs * 16), kThreads, smem_c, st>>>(spec, S, d_rows, cw);
+    WTB_LAUNCH_CHECK();
+  }
   if (d_hist) {
     WTB_CUDA(cudaFuncSetAttribute(k_wct_coh_4096<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     k_wct_coh_4096<1><<<(unsigned)nrows, kThreads, smem_b, st>>>(spec, n0, S, d_rows, tw2, tw3, cw, nullptr,

@@ -279,9 +279,7 @@ static int xwt_wct_entry(const void *y1, const void *y2, int64_t batch, int n0, 
       if (w12_out)
         WTB_CUDA(cudaMemcpyAsync((cplx<T> *)w12_out + b0 * plane, d_w12, sizeof(cplx<T>) * nb * plane, out_kind, st));
       WTB_CUDA(cudaStreamSynchronize(st));
-    } else if (b0 + rows < batch) {
-      WTB_CUDA(cudaStreamSynchronize(st));  // arena reuse across chunks
-    }
+    }  // device buffers: chunks reuse the arena without a host sync (all work is ordered on `st`)
   }
   return WTB_OK;
 }
@@ -343,7 +341,7 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
     }
     WTB_TRY(wct_device<T>(src, nb, nsurr, N, dt, dj, ax, f0, nullptr, nullptr, nullptr, hist_dev,
                           tlo.data(), thi.data(), maxscale, st));
-    if (m0 + rows < mc_count) WTB_CUDA(cudaStreamSynchronize(st));  // arena reuse across chunks
+    // chunks reuse the arena without a host sync: every kernel and copy is ordered on `st`
   }
   if (!dev) {
     std::vector<uint64_t> h((size_t)S * WTB_NBINS);

@@ -34,6 +34,7 @@ using fft16::br4;
 constexpr int kN = 4096;
 constexpr int kThreads = 256;
 constexpr int kBuf = kN + kN / 16;     // padded: index i lives at i + (i >> 4)
+constexpr int kMaxRowsC = 512;         // scale rows the boxcar kernel stages in shared memory
 
 struct WRow {
   float a;        // (s/dt) * 2*pi/N : s*w_k = a*k
@@ -196,37 +197,53 @@ __global__ void __launch_bounds__(kThreads)
 k_wct_boxcar_4096(float4 *__restrict__ spec, int S, const WRow *__restrict__ rows, CohWin win) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *ring = reinterpret_cast<float4 *>(smem_raw);     // [K][kThreads]
+  __shared__ int s_kc[kMaxRowsC];
   const int tid = threadIdx.x;
+  for (int q = tid; q < S; q += kThreads) s_kc[q] = rows[q].kc;
+  __syncthreads();
   const int64_t pair = blockIdx.x >> 4;
   const int bin = ((blockIdx.x & 15) << 8) + tid;
   const int akk = bin < kN / 2 ? bin : kN - bin;
-  if (akk > rows[0].kc) return;                            // outside every row's pass band
+  if (akk > s_kc[0]) return;                               // outside every row's pass band
+  // pass bands shrink with scale: rows 0 .. s_max hold this bin
+  int s_max = 0;
+  while (s_max + 1 < S && akk <= s_kc[s_max + 1]) ++s_max;
   float4 *col = spec + pair * (int64_t)S * kN + bin;
   const int K = win.K, up = win.up;
   const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   for (int k = 0; k < K; ++k) ring[k * kThreads + tid] = zero;
+  // outputs i <= s_max + (K-1) - up are the only ones whose window still holds this bin
+  const int s_end = min(S + up, s_max + K);
   int slot = 0;                                             // ring slot of input row s_in
-  for (int s_in = 0; s_in < S + up; ++s_in) {
-    float4 v = zero;
-    if (s_in < S && akk <= rows[s_in].kc) v = col[(int64_t)s_in * kN];
-    ring[slot * kThreads + tid] = v;
-    const int i = s_in - up;                                // output row completed by this input
-    if (i >= 0) {
-      const int first = i + up - (K - 1);                   // smallest-scale row of the window
-      if (akk <= rows[first < 0 ? 0 : first].kc) {
-        float4 acc = zero;
-        int sl = slot;                                      // k = 0 <-> row i + up = s_in
-        for (int k = 0; k < K; ++k) {
-          const float4 g = ring[sl * kThreads + tid];
-          const float w = win.w[k];
-          acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
-          acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
-          sl = sl == 0 ? K - 1 : sl - 1;
+  for (int s0 = 0; s0 < s_end; s0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)                             // four independent loads in flight
+      v[q] = (s0 + q <= s_max) ? col[(int64_t)(s0 + q) * kN] : zero;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s_in = s0 + q;
+      if (s_in < s_end) {
+        ring[slot * kThreads + tid] = v[q];
+        const int i = s_in - up;                            // output row completed by this input
+        if (i >= 0 && i < S) {
+          const int first = i + up - (K - 1);               // smallest-scale row of the window
+          if (akk <= s_kc[first < 0 ? 0 : first]) {
+            float4 acc = zero;
+            int sl = slot;                                  // k = 0 <-> row i + up = s_in
+            for (int k = 0; k < K; ++k) {
+              const float4 g = ring[sl * kThreads + tid];
+              const float w = win.w[k];
+              acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
+              acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+              sl = sl == 0 ? K - 1 : sl - 1;
+            }
+            col[(int64_t)i * kN] = acc;
+          }
         }
-        col[(int64_t)i * kN] = acc;
+        slot = slot + 1 == K ? 0 : slot + 1;
       }
     }
-    slot = slot + 1 == K ? 0 : slot + 1;
   }
 }
 
@@ -344,7 +361,7 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
                  float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
                  const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32) return 1;
+  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32 || S > kMaxRowsC) return 1;
   const bool smooth = d_wct || d_hist;
   std::vector<WRow> rows(S);
   for (int s = 0; s < S; ++s) {

@@ -91,3 +91,17 @@ def test_wavedec_batch_fp32(shim):
     assert np.abs(packed - ref).max() < 1e-5
     rec = shim.waverec(packed, lens, rlo, rhi, f64=False)
     assert np.abs(rec - x).max() < 1e-5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("f64", [True, False])
+def test_imodwt_tma_path_many_ctas(shim, f64):
+    """Regression: 16-byte-aligned rows take the TMA (cp.async.bulk + mbarrier) path, and
+    imodwt re-arms the barrier once per level.  With thousands of CTAs a thread lagging a
+    whole barrier phase used to deadlock."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((20000, 1024))
+    lo, hi, _, _ = _bank("sym4")
+    w = shim.modwt(x, lo, hi, 6, f64=f64)
+    rec = shim.imodwt(w, lo, hi, f64=f64)
+    assert np.abs(rec - x).max() < (1e-10 if f64 else 1e-4)

@@ -306,6 +306,28 @@ def modwt(x, g, h, J, *, f64=None):
     return out[0] if np.ndim(x) == 1 else out
 
 
+def modwt_device(x_ptr, batch, n, g, h, J, out_ptr, *, f64=False, stream=0):
+    """Device-resident MODWT: x [batch, n] -> out [batch, J+1, n], asynchronous on `stream`."""
+    g, h = _taps(g, h)
+    _check(lib().wtb_modwt(_ptr(int(x_ptr)), batch, n, _dp(g), _dp(h), g.size, int(J),
+                           DEVICE_PTRS | (F64 if f64 else 0), _ptr(int(out_ptr)), C.c_void_p(int(stream))),
+           "wtb_modwt")
+
+
+def imodwt_device(w_ptr, batch, n, g, h, J, out_ptr, *, f64=False, stream=0):
+    g, h = _taps(g, h)
+    _check(lib().wtb_imodwt(_ptr(int(w_ptr)), batch, n, _dp(g), _dp(h), g.size, int(J),
+                            DEVICE_PTRS | (F64 if f64 else 0), _ptr(int(out_ptr)), C.c_void_p(int(stream))),
+           "wtb_imodwt")
+
+
+def wavedec_device(x_ptr, batch, n, dec_lo, dec_hi, level, out_ptr, *, f64=False, stream=0):
+    lo, hi = _taps(dec_lo, dec_hi)
+    _check(lib().wtb_wavedec(_ptr(int(x_ptr)), batch, n, _dp(lo), _dp(hi), lo.size, int(level),
+                             DEVICE_PTRS | (F64 if f64 else 0), _ptr(int(out_ptr)), C.c_void_p(int(stream))),
+           "wtb_wavedec")
+
+
 def imodwt(w, g, h, *, f64=None):
     f64 = _resolve_f64(f64)
     g, h = _taps(g, h)

@@ -59,38 +59,69 @@ __device__ void stage_row(T *dst, const T *__restrict__ src, int n, uint64_t *ba
     }
     mbar_wait(bar, phase);
     phase ^= 1;
+    // No thread may lag a whole phase behind: if thread 0 re-armed the barrier and the next
+    // copy landed before a slow thread had tested this phase, that thread would wait forever.
+    __syncthreads();
   } else {
     for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = src[t];
     __syncthreads();
   }
 }
 
-// ---- MODWT analysis: w_j[t] = sum_l h[l] v[(t - 2^(j-1) l) mod N] ---------------------
+// Filter taps (in precision T) and the per-level circular offsets (2^(j-1) l) mod N live in
+// shared memory: the inner loops are then one LDS + compare + 2 FMA per tap, with no
+// integer division and no double->T conversion.
+template <typename T> struct TapSmem {
+  T lo[kMaxTaps];
+  T hi[kMaxTaps];
+  int off[kMaxTaps];
+};
+
 template <typename T>
+__device__ __forceinline__ void load_taps(TapSmem<T> &ts, const Taps &taps) {
+  if (threadIdx.x < taps.L) {
+    ts.lo[threadIdx.x] = T(taps.lo[threadIdx.x]);
+    ts.hi[threadIdx.x] = T(taps.hi[threadIdx.x]);
+  }
+}
+// call with all threads; ends with a barrier
+template <typename T>
+__device__ __forceinline__ void set_offsets(TapSmem<T> &ts, int L, int j, int n) {
+  if (threadIdx.x < L) ts.off[threadIdx.x] = (int)(((1LL << (j - 1)) * threadIdx.x) % n);
+  __syncthreads();
+}
+
+// ---- MODWT analysis: w_j[t] = sum_l h[l] v[(t - 2^(j-1) l) mod N] ---------------------
+// LT: compile-time tap count (0 = runtime taps.L)
+template <typename T, int LT>
 __global__ void k_modwt(const T *__restrict__ x, int n, int J, Taps taps, T *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ TapSmem<T> ts;
   T *v = reinterpret_cast<T *>(smem_raw);
   T *vn = v + ((n + 3) & ~3);
   const int64_t b = blockIdx.x;
+  const int L = LT ? LT : taps.L;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  load_taps(ts, taps);
   __syncthreads();
   uint32_t phase = 0;
   stage_row<T>(v, x + b * n, n, &bar, phase);
   T *o = out + b * (int64_t)(J + 1) * n;
   for (int j = 1; j <= J; ++j) {
-    const long long stride = 1LL << (j - 1);
+    set_offsets(ts, L, j, n);
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
       T w = 0, s = 0;
-      for (int l = 0; l < taps.L; ++l) {
-        int idx = t - (int)((stride * l) % n);
-        if (idx < 0) idx += n;
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        int idx = t - ts.off[l];
+        idx += idx < 0 ? n : 0;
         const T val = v[idx];
-        w += T(taps.hi[l]) * val;
-        s += T(taps.lo[l]) * val;
+        w = fma(ts.hi[l], val, w);
+        s = fma(ts.lo[l], val, s);
       }
       o[(int64_t)(j - 1) * n + t] = w;
       vn[t] = s;
@@ -102,33 +133,37 @@ __global__ void k_modwt(const T *__restrict__ x, int n, int J, Taps taps, T *__r
 }
 
 // ---- MODWT synthesis: v_{j-1}[t] = sum_l h[l] w_j[(t+2^(j-1) l) mod N] + g[l] v_j[...] ---
-template <typename T>
+template <typename T, int LT>
 __global__ void k_imodwt(const T *__restrict__ w, int n, int J, Taps taps, T *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ TapSmem<T> ts;
   const int np = (n + 3) & ~3;
   T *v = reinterpret_cast<T *>(smem_raw);
   T *vn = v + np;
   T *wj = vn + np;
   const int64_t b = blockIdx.x;
+  const int L = LT ? LT : taps.L;
   const T *wb = w + b * (int64_t)(J + 1) * n;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  load_taps(ts, taps);
   __syncthreads();
   uint32_t phase = 0;
   stage_row<T>(v, wb + (int64_t)J * n, n, &bar, phase);
   for (int j = J; j >= 1; --j) {
     stage_row<T>(wj, wb + (int64_t)(j - 1) * n, n, &bar, phase);
-    const long long stride = 1LL << (j - 1);
+    set_offsets(ts, L, j, n);
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
       T acc_h = 0, acc_g = 0;
-      for (int l = 0; l < taps.L; ++l) {
-        int idx = t + (int)((stride * l) % n);
-        if (idx >= n) idx -= n;
-        acc_h += T(taps.hi[l]) * wj[idx];
-        acc_g += T(taps.lo[l]) * v[idx];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        int idx = t + ts.off[l];
+        idx -= idx >= n ? n : 0;
+        acc_h = fma(ts.hi[l], wj[idx], acc_h);
+        acc_g = fma(ts.lo[l], v[idx], acc_g);
       }
       vn[t] = acc_h + acc_g;
     }
@@ -173,6 +208,9 @@ __global__ void k_modwtmra(const T *__restrict__ w, int n, int J, const double *
 // ---- DWT (symmetric) ---------------------------------------------------------------------
 __device__ __forceinline__ int reflect_sym(int p, int n) {
   // half-sample symmetric extension, repeated when |p| runs past one period
+  if (p >= 0 && p < n) return p;
+  if (p < 0 && p >= -n) return -1 - p;          // one reflection covers every level with n >= L
+  if (p >= n && p < 2 * n) return 2 * n - 1 - p;
   const int period = 2 * n;
   int m = p % period;
   if (m < 0) m += period;
@@ -308,10 +346,11 @@ template <typename T>
 static int modwt_impl(const void *x, int64_t batch, int n, const Taps &taps, int J, int flags, void *out,
                       cudaStream_t st) {
   const size_t smem = sizeof(T) * 2 * (size_t)((n + 3) & ~3);
-  WTB_TRY(set_smem(k_modwt<T>, smem));
+  auto kern = taps.L == 8 ? k_modwt<T, 8> : taps.L == 4 ? k_modwt<T, 4> : taps.L == 2 ? k_modwt<T, 2> : k_modwt<T, 0>;
+  WTB_TRY(set_smem(kern, smem));
   return run_batched(x, out, batch, sizeof(T) * n, sizeof(T) * (size_t)(J + 1) * n, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
-                       k_modwt<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
+                       kern<<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
                        WTB_LAUNCH_CHECK();
                        return WTB_OK;
                      });
@@ -321,10 +360,11 @@ template <typename T>
 static int imodwt_impl(const void *w, int64_t batch, int n, const Taps &taps, int J, int flags, void *out,
                        cudaStream_t st) {
   const size_t smem = sizeof(T) * 3 * (size_t)((n + 3) & ~3);
-  WTB_TRY(set_smem(k_imodwt<T>, smem));
+  auto kern = taps.L == 8 ? k_imodwt<T, 8> : taps.L == 4 ? k_imodwt<T, 4> : taps.L == 2 ? k_imodwt<T, 2> : k_imodwt<T, 0>;
+  WTB_TRY(set_smem(kern, smem));
   return run_batched(w, out, batch, sizeof(T) * (size_t)(J + 1) * n, sizeof(T) * n, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
-                       k_imodwt<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
+                       kern<<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
                        WTB_LAUNCH_CHECK();
                        return WTB_OK;
                      });

@@ -322,7 +322,7 @@ def run_gpu(args):
         del xh, ph
     else:
         # host-facing call: histogram accumulated on device, copied back and reduced to thresholds each step
-        Re = max(64, args.realisations // 8)
+        Re = args.realisations   # same batch as the device-resident step: the call is not copy-bound
         t0 = time.perf_counter()
         for k in range(args.e2e_steps):
             h = _shim.wct_mc_hist(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], MC["f0"],

@@ -69,6 +69,15 @@ int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft,
                    double dt, double dj, double s0, int J, double f0, int flags,
                    void *power_out, void *coef_out, void *stream);
 
+/* ---- batched pre-processing: replaces standardize_series (src/utils/wavelet_helpers.py:22-57)
+ * and pycwt.ar1 (src/cwt.py:106) for batches of series ------------------------------------ */
+/* x: [batch, n] real.  y_out (may be NULL): [batch, n] = optional degree-1 detrend or mean
+ * removal, then division by the RAW series' population standard deviation.  ar1_out (may be
+ * NULL): [batch] lag-1 autocorrelation of the INPUT series (Allen & Smith), NaN where pycwt
+ * raises "Cannot place an upperbound on the unbiased AR(1)". */
+int wtb_series_prep(const void *x, int64_t batch, int n, int detrend, int remove_mean, int standardize,
+                    int flags, void *y_out, double *ar1_out, void *stream);
+
 /* ---- XWT / WCT: replaces pycwt.xwt (src/xwt.py:93) and pycwt.wct
  * (src/wct.py:106, src/xwt.py:122) minus the host-side normalisation ------- */
 /* y1, y2: [batch, n0] real (already normalised by the caller).  Outputs (any

@@ -14,6 +14,15 @@ if str(ROOT) not in sys.path:
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
+def pytest_sessionstart(session):
+    """Make sure libwavelet_sm100a.so exists and is current (nvcc cross-compiles without a GPU);
+    on a box without nvcc the prebuilt library that travelled with the snapshot is used."""
+    import shutil
+    if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists():
+        from wavelet_transformer_b200 import _build
+        _build.build(force=False)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) and the built libwavelet_sm100a.so")
 

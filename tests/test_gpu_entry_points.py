@@ -184,3 +184,46 @@ def test_pycwt_facade_cwt_side_outputs(series):
     assert np.allclose(fft_, ffto) and np.allclose(fftfreqs, fqo)
     with pytest.raises(NotImplementedError):
         wavelet.cwt(x, DT, wavelet="paul")
+
+
+def test_series_prep_matches_reference_helpers(shim, series, helpers_golden):
+    """Batched standardize_series + ar1 (wtb_series_prep) against the reference's own
+    standardize_series outputs (golden) and the ar1 oracle."""
+    g = helpers_golden
+    y, a = shim.series_prep(g["y"], detrend=True, f64=True)
+    assert np.abs(y - g["std_detrend"]).max() <= 1e-10 * np.abs(g["std_detrend"]).max()
+    y, _ = shim.series_prep(g["y"], detrend=False, remove_mean=True, f64=True)
+    assert np.abs(y - g["std_mean"]).max() <= 1e-12
+    y, _ = shim.series_prep(g["y"], detrend=False, standardize=False, f64=True)
+    assert np.array_equal(y, g["std_raw"])
+    assert np.isnan(a)                                        # pair_inflation: pycwt.ar1 raises
+    batch = np.stack([series["expectation_value"], (100 * np.diff(np.log(series["cpi_value"])))[-565:],
+                      series["pair_inflation"]])
+    _, ar = shim.series_prep(batch, f64=True, want_y=False)
+    assert ar[0] == pytest.approx(po.ar1(batch[0])[0], rel=1e-11)
+    assert ar[1] == pytest.approx(po.ar1(batch[1])[0], rel=1e-11)
+    assert np.isnan(ar[2])
+    y32, ar32 = shim.series_prep(batch, f64=False)
+    assert y32.dtype == np.float32 and ar32[0] == pytest.approx(po.ar1(batch[0])[0], rel=1e-5)
+    with pytest.raises(ValueError):
+        shim.series_prep(batch, detrend=True, remove_mean=True)
+
+
+def test_cwt_batch_resident(shim, series):
+    """Device-resident standardize -> ar1 -> CWT -> significance ratio vs the host pipeline."""
+    import torch
+    from src import cwt
+    from wavelet_transformer_b200 import engine
+    d = 100 * np.diff(np.log(series["cpi_value"]))
+    x = torch.tensor(np.stack([d[:1024], d[-1024:], d[100:1124]]), dtype=torch.float64, device="cuda")
+    out = engine.cwt_batch_resident(x, cwt.DT, cwt.DJ, cwt.S0, 84, significance_level=0.95)
+    torch.cuda.synchronize()
+    for b in range(3):
+        xb = x[b].cpu().numpy()
+        data = cwt.DataForCWT(_dates(series["cpi_days"])[:1024], xb, cwt.MOTHER, cwt.DT, cwt.DJ, cwt.S0, cwt.LEVELS)
+        ref = cwt.run_cwt(data, standardize=True, detrend=True)
+        got = out["power"][b].cpu().numpy()
+        assert np.abs(got - ref.power).max() <= 1e-9 * ref.power.max()
+        ratio = got / out["signif"][b].cpu().numpy()[:, None]
+        assert np.abs(ratio - ref.significance_levels).max() <= 1e-8 * ref.significance_levels.max()
+        assert float(out["ar1"][b]) == pytest.approx(po.ar1(xb)[0], rel=1e-10)

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "wtb_kernel_launches": ([], C.c_uint64),
     "wtb_cwt_axes": ([_i32, _f64, _f64, _f64, _i32, _f64, _pi, _pd, _pd, _pd], _i32),
     "wtb_cwt_morlet": ([_vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp], _i32),
+    "wtb_series_prep": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _pd, _vp], _i32),
     "wtb_xwt_wct": ([_vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp, _vp], _i32),
     "wtb_wct_mc_geometry": ([_f64, _f64, _f64, _i32, _f64, _pi, _pi], _i32),
     "wtb_wct_mc_hist": ([_f64, _f64, _f64, _f64, _f64, _i32, _f64, _i64, _i64, _u64, _vp, _i32, _vp, _vp], _i32),
@@ -189,6 +190,32 @@ def cwt_power_device(x_ptr, batch, n0, dt, dj, s0, J, f0, power_ptr, *, nfft=Non
     flags = DEVICE_PTRS | (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0)
     _check(lib().wtb_cwt_morlet(_ptr(int(x_ptr)), batch, n0, nfft, dt, dj, s0, int(J), f0, flags,
                                 _ptr(int(power_ptr)), None, C.c_void_p(int(stream))), "wtb_cwt_morlet")
+
+
+def series_prep(x, *, detrend=True, remove_mean=False, standardize=True, f64=None, want_y=True, want_ar1=True):
+    """Batched standardize_series + pycwt.ar1 of host data.  x: [n] or [batch, n].
+    Returns (y or None, ar1 or None); ar1 is NaN where the estimate cannot be bounded."""
+    f64 = _resolve_f64(f64)
+    x2 = np.ascontiguousarray(np.atleast_2d(np.asarray(x)), dtype=_dtype(f64))
+    batch, n = x2.shape
+    y = np.empty_like(x2) if want_y else None
+    a = np.empty(batch) if want_ar1 else None
+    _check(lib().wtb_series_prep(_ptr(x2), batch, n, int(detrend), int(remove_mean), int(standardize),
+                                 F64 if f64 else 0, _ptr(y), None if a is None else _dp(a), None),
+           "wtb_series_prep")
+    if np.ndim(x) == 1:
+        y = None if y is None else y[0]
+        a = None if a is None else a[0]
+    return y, a
+
+
+def series_prep_device(x_ptr, batch, n, y_ptr, ar1_ptr, *, detrend=True, remove_mean=False, standardize=True,
+                       f64=False, stream=0):
+    """Device-resident variant (y_ptr / ar1_ptr may be 0 for "not wanted")."""
+    _check(lib().wtb_series_prep(_ptr(int(x_ptr)), batch, n, int(detrend), int(remove_mean), int(standardize),
+                                 DEVICE_PTRS | (F64 if f64 else 0), C.c_void_p(int(y_ptr)) if y_ptr else None,
+                                 C.cast(C.c_void_p(int(ar1_ptr)), _pd) if ar1_ptr else None,
+                                 C.c_void_p(int(stream))), "wtb_series_prep")
 
 
 # ---------------------------------------------------------------- XWT / WCT

@@ -52,6 +52,39 @@ def cwt_power_resident(x, power, dt, dj, s0, J, f0=6.0, generic_only=False):
     return power
 
 
+def cwt_batch_resident(x, dt, dj, s0, J, f0=6.0, detrend=True, remove_mean=False, standardize=True,
+                       significance_level=None):
+    """Device-resident batch version of the reference's CWT request (src/wavelet_plots.py:32
+    -> src/cwt.py:85): standardize_series -> ar1 -> cwt -> |W|^2 [-> power / significance].
+
+    x: torch CUDA tensor [batch, n0] (float32 or float64).  Returns a dict of device tensors:
+    ``power`` [batch, J+1, n0], ``ar1`` [batch] (NaN where pycwt.ar1 would raise), and, when
+    ``significance_level`` is given, ``signif`` [batch, J+1] with ``power / signif[..., None]``
+    being the ratio run_cwt returns.  Nothing leaves the GPU."""
+    import torch
+    if not (x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.float64)):
+        raise ValueError("x must be a contiguous CUDA float32/float64 tensor")
+    batch, n0 = x.shape
+    f64 = x.dtype == torch.float64
+    stream = torch.cuda.current_stream().cuda_stream
+    y = torch.empty_like(x)
+    ar1 = torch.empty(batch, dtype=torch.float64, device=x.device)
+    _shim.series_prep_device(x.data_ptr(), batch, n0, y.data_ptr(), ar1.data_ptr(), detrend=detrend,
+                             remove_mean=remove_mean, standardize=standardize, f64=f64, stream=stream)
+    Jr, scales, freqs, coi = _shim.cwt_axes(n0, dt, dj, s0, J, f0)
+    power = torch.empty((batch, Jr + 1, n0), dtype=x.dtype, device=x.device)
+    cwt_power_resident(y, power, dt, dj, s0, Jr, f0)
+    out = {"power": power, "ar1": ar1, "scales": scales, "period": 1.0 / freqs, "coi": coi}
+    if significance_level is not None:
+        # pycwt.significance(1.0, dt, scales, 0, alpha): red-noise spectrum x chi2(2)/2, per series
+        fl = 4 * np.pi / (f0 + np.sqrt(2 + f0 ** 2))
+        freq = torch.as_tensor(dt / (scales * fl), device=x.device)[None, :]
+        a = ar1[:, None]
+        theor = (1 - a ** 2) / (1 + a ** 2 - 2 * a * torch.cos(2 * np.pi * freq))
+        out["signif"] = theor * (-np.log1p(-significance_level))
+    return out
+
+
 def wct_hist_resident(hist, a1, a2, dt, dj, s0, J, f0, mc_first, mc_count, seed, f64=False, white=False):
     """Add the coherence histograms of realisations [mc_first, mc_first+mc_count)
     to the device int64 tensor `hist` [J+1, 1000] (bit-identical to uint64)."""

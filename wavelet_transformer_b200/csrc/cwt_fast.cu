@@ -70,6 +70,13 @@ __device__ __forceinline__ float ex2(float x) {
 
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 
+// For a power of two M:  m < M  <=>  M > below_pow2(m), with below_pow2(m) the largest
+// power of two <= m (and -1 for m = 0).  Unrolled loops over m then test M against only
+// log2 distinct constants, one compare per block [2^k, 2^(k+1)).
+__device__ __forceinline__ constexpr int below_pow2(int m) {
+  return m == 0 ? -1 : (m < 2 ? 1 : (m < 4 ? 2 : (m < 8 ? 4 : 8)));
+}
+
 // One dit32 call site serves the forward transform (s = -1), step A and step B of
 // every scale row: the hot code stays inside the instruction cache.
 __global__ void __launch_bounds__(kWarps * 32, 1)
@@ -126,9 +133,10 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           const float2 zl2 = make_float2(zl, fmaf(rp.a, 32.0f, zl));
           const float2 a64 = bc(rp.a * 64.0f);
           const float2 ln2 = bc(rp.lognorm);
+          // M is a power of two: blocks [0,1), [1,2), [2,4), [4,8) need one branch each
 #pragma unroll
           for (int m = 0; m < 8; ++m) {
-            if (m < M) {
+            if (M > below_pow2(m)) {
               const float2 z = fma2(a64, bc((float)m), zl2);
               const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);   // -0.5*log2(e)*z^2 + log2(norm)
               const float2 d = make_float2(ex2(e.x), ex2(e.y));
@@ -147,7 +155,7 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           const int M = 1 << (rp.L - 1);
 #pragma unroll
           for (int m = 0; m < 16; ++m) {
-            if (m < M) {
+            if (M > below_pow2(m)) {
               const float2 yr = *reinterpret_cast<const float2 *>(&ws.yr[2 * m]);
               const float2 yi = *reinterpret_cast<const float2 *>(&ws.yi[2 * m]);
               const float4 t = sm.tw_b[m][lane];

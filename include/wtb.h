@@ -123,6 +123,14 @@ int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, const doubl
  * modwt.py:56-83); out[b,j,t] = sum_l filt[j,l] * w[b,j,(t+l) mod n]. */
 int wtb_modwtmra(const void *w, int64_t batch, int n, const double *filt, int J,
                  int flags, void *out, void *stream);
+/* Same details D_1..D_J and smooth S_J from the taps alone (modwt.py:163-194):
+ * each row runs the synthesis cascade G_1'..G_{j-1}' H_j' w_j, which equals the
+ * correlation with the periodised equivalent filter.  Shapes the cascade
+ * kernel does not cover (L not in {2,4,6,8}, dilated filter longer than n)
+ * are served by building those filters on the host and correlating. */
+int wtb_modwtmra_taps(const void *w, int64_t batch, int n, const double *g,
+                      const double *h, int L, int J, int flags, void *out,
+                      void *stream);
 
 /* ---- DWT: replaces pywt.wavedec / pywt.waverec (src/dwt.py:104,71,120) ---- */
 /* lens: [level+1] lengths of cA_L, cD_L, ..., cD_1 for symmetric mode. */

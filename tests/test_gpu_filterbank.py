@@ -105,3 +105,94 @@ def test_imodwt_tma_path_many_ctas(shim, f64):
     w = shim.modwt(x, lo, hi, 6, f64=f64)
     rec = shim.imodwt(w, lo, hi, f64=f64)
     assert np.abs(rec - x).max() < (1e-10 if f64 else 1e-4)
+
+
+# ---- register-blocked kernels (csrc/filterbank_fast.cu) vs the generic ones and the oracle ----
+@pytest.mark.parametrize("name", ["haar", "db2", "db3", "db4", "sym4"])
+@pytest.mark.parametrize("n,J", [(23, 6), (64, 4), (565, 6), (1000, 7), (1333, 6), (4096, 9)])
+def test_modwt_blocked_kernels_fp64(shim, name, n, J):
+    """Chains of 9 outputs at stride 2^(j-1): aligned (TMA) and odd (cooperative) rows, tails that
+    do not fill a chain, and dilated filters longer than the series (n=23, J=6)."""
+    rng = np.random.default_rng(n + J)
+    x = rng.standard_normal((3, n))
+    lo, hi, _, _ = _bank(name)
+    ref = np.stack([mo.modwt(r, name, J) for r in x])
+    w = shim.modwt(x, lo, hi, J, f64=True)
+    assert np.abs(w - ref).max() <= 1e-12
+    assert np.abs(w - shim.modwt(x, lo, hi, J, f64=True, generic_only=True)).max() <= 1e-13
+    rec = shim.imodwt(w, lo, hi, f64=True)
+    assert np.abs(rec - x).max() <= 1e-10
+    assert np.abs(rec - shim.imodwt(w, lo, hi, f64=True, generic_only=True)).max() <= 1e-12
+    mra = shim.modwtmra_taps(w, lo, hi, f64=True)
+    mra_ref = np.stack([mo.modwtmra(r, name) for r in ref])
+    assert np.abs(mra - mra_ref).max() <= 1e-11
+    assert np.abs(mra.sum(axis=1) - x).max() <= 1e-10
+
+
+def test_modwt_unblocked_tap_count_falls_back(shim):
+    """L = 10 has no blocked instantiation: the generic kernels serve it, and the taps-only
+    MRA entry point builds the periodised equivalent filters itself (modwt.py:56-83)."""
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((2, 300))
+    lo, hi, _, _ = _bank("db5")
+    w = shim.modwt(x, lo, hi, 4, f64=True)
+    assert np.abs(w - np.stack([mo.modwt(r, "db5", 4) for r in x])).max() <= 1e-12
+    assert np.abs(shim.imodwt(w, lo, hi, f64=True) - x).max() <= 1e-10
+    mra = shim.modwtmra_taps(w, lo, hi, f64=True)
+    assert np.abs(mra[0] - mo.modwtmra(w[0], "db5")).max() <= 1e-11
+    from wavelet_transformer_b200.api import modwt as api
+    assert np.abs(api.modwtmra(w[1], "db5") - mo.modwtmra(w[1], "db5")).max() <= 1e-11
+    # the same host-built filters serve a covered tap count when the cascade is switched off
+    lo4, hi4, _, _ = _bank("sym4")
+    w4 = shim.modwt(x, lo4, hi4, 5, f64=True)
+    a = shim.modwtmra_taps(w4, lo4, hi4, f64=True)
+    b = shim.modwtmra_taps(w4, lo4, hi4, f64=True, generic_only=True)
+    c = shim.modwtmra(w4, np.vstack(mo.mra_filters("sym4", 5, 300)), f64=True)
+    assert np.abs(a - b).max() <= 1e-12 and np.abs(b - c).max() <= 1e-13
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_modwt_blocked_large_batch(shim, f64):
+    """TMA bulk stores of every coefficient row, double buffered, thousands of CTAs."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((6000, 1024))
+    lo, hi, _, _ = _bank("sym4")
+    w = shim.modwt(x, lo, hi, 6, f64=f64)
+    tol = 1e-12 if f64 else 2e-5
+    for b in (0, 17, 5999):
+        assert np.abs(w[b] - mo.modwt(x[b], "sym4", 6)).max() <= tol
+    assert np.abs(w - shim.modwt(x, lo, hi, 6, f64=f64, generic_only=True)).max() <= (1e-13 if f64 else 1e-5)
+    mra = shim.modwtmra_taps(w, lo, hi, f64=f64)
+    assert np.abs(mra.sum(axis=1) - x).max() <= (1e-10 if f64 else 1e-4)
+    for b in (3, 5998):
+        assert np.abs(mra[b] - mo.modwtmra(np.asarray(w[b], dtype=float), "sym4")).max() <= (1e-11 if f64 else 1e-4)
+
+
+@pytest.mark.parametrize("name", ["haar", "db2", "db3", "db4"])
+@pytest.mark.parametrize("n", [23, 64, 565, 1024, 1333])
+def test_dwt_blocked_vs_generic_fp64(shim, name, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((5, n))
+    lo, hi, rlo, rhi = _bank(name)
+    level = pw.dwt_max_level(n, lo.size)
+    if level == 0:
+        pytest.skip("series too short for this filter")
+    packed, lens = shim.wavedec(x, lo, hi, level, f64=True)
+    packed_g, _ = shim.wavedec(x, lo, hi, level, f64=True, generic_only=True)
+    ref = np.stack([np.concatenate(pw.wavedec(r, name, level=level)) for r in x])
+    assert np.abs(packed - ref).max() <= 1e-12 and np.abs(packed - packed_g).max() <= 1e-13
+    rec = shim.waverec(packed, lens, rlo, rhi, f64=True)
+    rec_g = shim.waverec(packed, lens, rlo, rhi, f64=True, generic_only=True)
+    assert rec.shape == rec_g.shape and np.abs(rec - rec_g).max() <= 1e-12
+    assert np.abs(rec[:, :n] - x).max() <= 1e-9 if n % 2 == 0 else rec.shape[1] == n + 1
+
+
+def test_dwt_blocked_large_batch_fp32(shim):
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((4000, 1024))
+    lo, hi, rlo, rhi = _bank("db4")
+    packed, lens = shim.wavedec(x, lo, hi, 7, f64=False)
+    for b in (0, 3999):
+        assert np.abs(packed[b] - np.concatenate(pw.wavedec(x[b], "db4", level=7))).max() < 2e-5
+    rec = shim.waverec(packed, lens, rlo, rhi, f64=False)
+    assert np.abs(rec - x).max() < 1e-4

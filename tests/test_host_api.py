@@ -96,7 +96,7 @@ def test_facade_closed_forms(series):
     assert m.flambda() == po.Morlet(6).flambda() and m.deltaj0 == 0.6 and m.name == "morlet"
     for cls in (wavelet.Paul, wavelet.DOG, wavelet.MexicanHat):
         assert cls().flambda() > 0          # constructible at import time, as the reference needs
-    for name in ("db4", "sym4", "haar", "db2"):
+    for name in ("db4", "sym4", "haar", "db2", "db3", "db5"):
         w, o = pywt.Wavelet(name), pw.Wavelet(name)
         assert w.dec_lo == o.dec_lo and w.dec_hi == o.dec_hi and w.rec_lo == o.rec_lo and w.dec_len == o.dec_len
     with pytest.raises(ValueError):

@@ -6,7 +6,7 @@ import pytest
 from oracle import pywt_oracle as pw
 
 
-@pytest.mark.parametrize("name", ["haar", "db2", "db4", "sym4"])
+@pytest.mark.parametrize("name", ["haar", "db2", "db3", "db4", "db5", "sym4"])
 def test_qmf_identities(name):
     w = pw.Wavelet(name)
     g, h = np.array(w.dec_lo), np.array(w.dec_hi)
@@ -45,7 +45,7 @@ def test_levels_and_lengths(series):
 
 
 @pytest.mark.parametrize("n", [64, 564, 1000])
-@pytest.mark.parametrize("name", ["haar", "db2", "db4", "sym4"])
+@pytest.mark.parametrize("name", ["haar", "db2", "db3", "db4", "db5", "sym4"])
 def test_perfect_reconstruction_even(n, name):
     x = np.random.default_rng(n).standard_normal(n)
     rec = pw.waverec(pw.wavedec(x, name), name)

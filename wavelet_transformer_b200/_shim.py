@@ -72,6 +72,7 @@ _SIGNATURES = {
     "wtb_modwt": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
     "wtb_imodwt": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
     "wtb_modwtmra": ([_vp, _i64, _i32, _pd, _i32, _i32, _vp, _vp], _i32),
+    "wtb_modwtmra_taps": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
     "wtb_dwt_coeff_lens": ([_i32, _i32, _i32, _pi], _i32),
     "wtb_dwt_max_level": ([_i32, _i32], _i32),
     "wtb_wavedec": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
@@ -322,14 +323,14 @@ def _taps(lo, hi):
     return lo, hi
 
 
-def modwt(x, g, h, J, *, f64=None):
+def modwt(x, g, h, J, *, f64=None, generic_only=False):
     f64 = _resolve_f64(f64)
     g, h = _taps(g, h)
     x2 = np.ascontiguousarray(np.atleast_2d(np.asarray(x)), dtype=_dtype(f64))
     batch, n = x2.shape
     out = np.empty((batch, J + 1, n), dtype=x2.dtype)
-    _check(lib().wtb_modwt(_ptr(x2), batch, n, _dp(g), _dp(h), g.size, int(J), F64 if f64 else 0,
-                           _ptr(out), None), "wtb_modwt")
+    _check(lib().wtb_modwt(_ptr(x2), batch, n, _dp(g), _dp(h), g.size, int(J),
+                           (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0), _ptr(out), None), "wtb_modwt")
     return out[0] if np.ndim(x) == 1 else out
 
 
@@ -355,15 +356,15 @@ def wavedec_device(x_ptr, batch, n, dec_lo, dec_hi, level, out_ptr, *, f64=False
            "wtb_wavedec")
 
 
-def imodwt(w, g, h, *, f64=None):
+def imodwt(w, g, h, *, f64=None, generic_only=False):
     f64 = _resolve_f64(f64)
     g, h = _taps(g, h)
     w = np.asarray(w)
     w3 = np.ascontiguousarray(w[None] if w.ndim == 2 else w, dtype=_dtype(f64))
     batch, rows, n = w3.shape
     out = np.empty((batch, n), dtype=w3.dtype)
-    _check(lib().wtb_imodwt(_ptr(w3), batch, n, _dp(g), _dp(h), g.size, rows - 1, F64 if f64 else 0,
-                            _ptr(out), None), "wtb_imodwt")
+    _check(lib().wtb_imodwt(_ptr(w3), batch, n, _dp(g), _dp(h), g.size, rows - 1,
+                            (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0), _ptr(out), None), "wtb_imodwt")
     return out[0] if w.ndim == 2 else out
 
 
@@ -381,6 +382,43 @@ def modwtmra(w, filt, *, f64=None):
     return out[0] if w.ndim == 2 else out
 
 
+def modwtmra_taps(w, g, h, *, f64=None, generic_only=False):
+    """MRA rows D_1..D_J, S_J from the wavelet taps (synthesis cascade, wtb_modwtmra_taps)."""
+    f64 = _resolve_f64(f64)
+    w = np.asarray(w)
+    w3 = np.ascontiguousarray(w[None] if w.ndim == 2 else w, dtype=_dtype(f64))
+    batch, rows, n = w3.shape
+    g, h = _taps(g, h)
+    out = np.empty_like(w3)
+    _check(lib().wtb_modwtmra_taps(_ptr(w3), batch, n, _dp(g), _dp(h), g.size, rows - 1,
+                                   (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0), _ptr(out), None),
+           "wtb_modwtmra_taps")
+    return out[0] if w.ndim == 2 else out
+
+
+def waverec_len(lens, L):
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    nout = lib().wtb_waverec_len(lens.ctypes.data_as(_pi), lens.size - 1, int(L))
+    if nout < 0:
+        _check(nout, "wtb_waverec_len")
+    return int(nout)
+
+
+def waverec_device(coeffs_ptr, batch, lens, rec_lo, rec_hi, out_ptr, *, f64=False, stream=0):
+    lo, hi = _taps(rec_lo, rec_hi)
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    _check(lib().wtb_waverec(_ptr(int(coeffs_ptr)), batch, lens.ctypes.data_as(_pi), lens.size - 1, _dp(lo), _dp(hi),
+                             lo.size, DEVICE_PTRS | (F64 if f64 else 0), _ptr(int(out_ptr)), C.c_void_p(int(stream))),
+           "wtb_waverec")
+
+
+def modwtmra_taps_device(w_ptr, batch, n, g, h, J, out_ptr, *, f64=False, stream=0):
+    g, h = _taps(g, h)
+    _check(lib().wtb_modwtmra_taps(_ptr(int(w_ptr)), batch, n, _dp(g), _dp(h), g.size, int(J),
+                                   DEVICE_PTRS | (F64 if f64 else 0), _ptr(int(out_ptr)), C.c_void_p(int(stream))),
+           "wtb_modwtmra_taps")
+
+
 def dwt_max_level(n, L):
     return int(lib().wtb_dwt_max_level(int(n), int(L)))
 
@@ -391,7 +429,7 @@ def dwt_coeff_lens(n, L, level):
     return lens
 
 
-def wavedec(x, dec_lo, dec_hi, level, *, f64=None):
+def wavedec(x, dec_lo, dec_hi, level, *, f64=None, generic_only=False):
     """Packed coefficients [batch, sum(lens)] + lens (cA_L, cD_L, ..., cD_1)."""
     f64 = _resolve_f64(f64)
     lo, hi = _taps(dec_lo, dec_hi)
@@ -399,12 +437,12 @@ def wavedec(x, dec_lo, dec_hi, level, *, f64=None):
     batch, n = x2.shape
     lens = dwt_coeff_lens(n, lo.size, level)
     out = np.empty((batch, int(lens.sum())), dtype=x2.dtype)
-    _check(lib().wtb_wavedec(_ptr(x2), batch, n, _dp(lo), _dp(hi), lo.size, int(level), F64 if f64 else 0,
-                             _ptr(out), None), "wtb_wavedec")
+    _check(lib().wtb_wavedec(_ptr(x2), batch, n, _dp(lo), _dp(hi), lo.size, int(level),
+                             (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0), _ptr(out), None), "wtb_wavedec")
     return (out[0] if np.ndim(x) == 1 else out), lens
 
 
-def waverec(packed, lens, rec_lo, rec_hi, *, f64=None):
+def waverec(packed, lens, rec_lo, rec_hi, *, f64=None, generic_only=False):
     f64 = _resolve_f64(f64)
     lo, hi = _taps(rec_lo, rec_hi)
     lens = np.ascontiguousarray(lens, dtype=np.int32)
@@ -418,5 +456,6 @@ def waverec(packed, lens, rec_lo, rec_hi, *, f64=None):
         _check(nout, "wtb_waverec_len")
     out = np.empty((p2.shape[0], nout), dtype=p2.dtype)
     _check(lib().wtb_waverec(_ptr(p2), p2.shape[0], lens.ctypes.data_as(_pi), level, _dp(lo), _dp(hi),
-                             lo.size, F64 if f64 else 0, _ptr(out), None), "wtb_waverec")
+                             lo.size, (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0), _ptr(out), None),
+           "wtb_waverec")
     return out[0] if p.ndim == 1 else out

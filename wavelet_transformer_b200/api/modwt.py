@@ -70,8 +70,9 @@ def mra_filters(filters, level, N):
 def modwtmra(w, filters):
     """Multiresolution analysis: details D_1..D_J and smooth S_J (modwt.py:163-194)."""
     w = np.asarray(w, dtype=float)
-    level, N = w.shape[0] - 1, w.shape[1]
-    return np.asarray(_shim.modwtmra(w, mra_filters(filters, level, N)), dtype=float)
+    g, h = _bank(filters)
+    # synthesis cascade on the device: same rows as the equivalent-filter correlation
+    return np.asarray(_shim.modwtmra_taps(w, g, h), dtype=float)
 
 
 def smooth_signal(modwt_coeffs: npt.NDArray, mother_wavelet: str, levels: int):

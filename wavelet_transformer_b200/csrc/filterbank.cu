@@ -5,68 +5,9 @@
 // bulk copy (cp.async.bulk + mbarrier) when it is 16-byte aligned, all pyramid
 // levels run out of shared memory, and only coefficients leave the SM.  These
 // paths are HBM-bound: bytes in = N, bytes out = (J+1) N per series.
-#include "common.cuh"
+#include "filterbank_common.cuh"
 
 namespace wtb {
-
-constexpr int kMaxTaps = 32;
-struct Taps {
-  int L;
-  double lo[kMaxTaps];  // scaling (g) taps as used by the kernel
-  double hi[kMaxTaps];  // wavelet (h) taps
-};
-
-// ---- TMA 1-D bulk load of `bytes` (multiple of 16, both sides 16B aligned) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(phase)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// Stage `n` elements of a row into shared memory.  All threads call it.
-template <typename T>
-__device__ void stage_row(T *dst, const T *__restrict__ src, int n, uint64_t *bar, uint32_t &phase) {
-  const size_t bytes = sizeof(T) * (size_t)n;
-  const bool tma_ok = (bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && bytes < (1u << 20);
-  if (tma_ok) {
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, (uint32_t)bytes);
-      tma_load_1d(dst, src, (uint32_t)bytes, bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    // No thread may lag a whole phase behind: if thread 0 re-armed the barrier and the next
-    // copy landed before a slow thread had tested this phase, that thread would wait forever.
-    __syncthreads();
-  } else {
-    for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = src[t];
-    __syncthreads();
-  }
-}
 
 // Filter taps (in precision T) and the per-level circular offsets (2^(j-1) l) mod N live in
 // shared memory: the inner loops are then one LDS + compare + 2 FMA per tap, with no
@@ -206,27 +147,6 @@ __global__ void k_modwtmra(const T *__restrict__ w, int n, int J, const double *
 }
 
 // ---- DWT (symmetric) ---------------------------------------------------------------------
-__device__ __forceinline__ int reflect_sym(int p, int n) {
-  // half-sample symmetric extension, repeated when |p| runs past one period
-  if (p >= 0 && p < n) return p;
-  if (p < 0 && p >= -n) return -1 - p;          // one reflection covers every level with n >= L
-  if (p >= n && p < 2 * n) return 2 * n - 1 - p;
-  const int period = 2 * n;
-  int m = p % period;
-  if (m < 0) m += period;
-  return m >= n ? period - 1 - m : m;
-}
-
-constexpr int kMaxLevels = 32;
-struct LevelPlan {
-  int level;
-  int n;                     // signal length (wavedec) / output length (waverec)
-  int buf;                   // elements per shared-memory ping-pong buffer
-  int total;                 // packed coefficient count per series
-  int len[kMaxLevels + 1];   // cA_L, cD_L, ..., cD_1
-  int off[kMaxLevels + 1];   // offsets of those blocks in the packed row
-};
-
 // cA[i] = sum_j lo[j] xe[2i+1-j]; cD with hi.  cA stays in smem for the next level.
 template <typename T>
 __global__ void k_wavedec(const T *__restrict__ x, LevelPlan plan, Taps taps, T *__restrict__ coeffs) {
@@ -312,34 +232,6 @@ static int make_taps(const double *lo, const double *hi, int L, double scale, Ta
   return WTB_OK;
 }
 
-// Runs `launch(d_in, d_out, rows)` over the batch, staging host buffers through the arena.
-template <typename F>
-static int run_batched(const void *in, void *out, int64_t batch, size_t in_row, size_t out_row,
-                       int flags, cudaStream_t st, F launch) {
-  if (flags & WTB_DEVICE_PTRS) return launch(in, out, batch);
-  const size_t budget = size_t(1) << 30;
-  const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(budget / (in_row + out_row))));
-  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  void *stage = nullptr;
-  WTB_TRY(staging_reserve(al(in_row * rows) + al(out_row * rows), &stage));
-  char *d_in = (char *)stage, *d_out = d_in + al(in_row * rows);
-  for (int64_t b0 = 0; b0 < batch; b0 += rows) {
-    const int64_t nb = std::min(rows, batch - b0);
-    WTB_CUDA(cudaMemcpyAsync(d_in, (const char *)in + b0 * in_row, in_row * nb, cudaMemcpyHostToDevice, st));
-    WTB_TRY(launch(d_in, d_out, nb));
-    WTB_CUDA(cudaMemcpyAsync((char *)out + b0 * out_row, d_out, out_row * nb, cudaMemcpyDeviceToHost, st));
-    WTB_CUDA(cudaStreamSynchronize(st));
-  }
-  return WTB_OK;
-}
-
-template <typename K> static int set_smem(K kernel, size_t bytes) {
-  WTB_REQUIRE(bytes <= 227 * 1024, WTB_EUNSUPPORTED,
-              "series too long for the in-shared-memory filterbank (%zu B > 227 KB per CTA)", bytes);
-  WTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return WTB_OK;
-}
-
 static int threads_for(int n) { return n >= 2048 ? 512 : (n >= 512 ? 256 : 128); }
 
 template <typename T>
@@ -347,9 +239,15 @@ static int modwt_impl(const void *x, int64_t batch, int n, const Taps &taps, int
                       cudaStream_t st) {
   const size_t smem = sizeof(T) * 2 * (size_t)((n + 3) & ~3);
   auto kern = taps.L == 8 ? k_modwt<T, 8> : taps.L == 4 ? k_modwt<T, 4> : taps.L == 2 ? k_modwt<T, 2> : k_modwt<T, 0>;
-  WTB_TRY(set_smem(kern, smem));
+  const bool fast = !(flags & WTB_GENERIC_ONLY) && fast_taps_ok(taps.L);
+  if (!fast) WTB_TRY(set_smem(kern, smem));
   return run_batched(x, out, batch, sizeof(T) * n, sizeof(T) * (size_t)(J + 1) * n, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
+                       if (fast) {
+                         const int rc = modwt_fast<T>(di, nb, n, taps, J, dout, st);
+                         if (rc != WTB_EUNSUPPORTED) return rc;
+                         WTB_TRY(set_smem(kern, smem));
+                       }
                        kern<<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
                        WTB_LAUNCH_CHECK();
                        return WTB_OK;
@@ -361,9 +259,15 @@ static int imodwt_impl(const void *w, int64_t batch, int n, const Taps &taps, in
                        cudaStream_t st) {
   const size_t smem = sizeof(T) * 3 * (size_t)((n + 3) & ~3);
   auto kern = taps.L == 8 ? k_imodwt<T, 8> : taps.L == 4 ? k_imodwt<T, 4> : taps.L == 2 ? k_imodwt<T, 2> : k_imodwt<T, 0>;
-  WTB_TRY(set_smem(kern, smem));
+  const bool fast = !(flags & WTB_GENERIC_ONLY) && fast_taps_ok(taps.L);
+  if (!fast) WTB_TRY(set_smem(kern, smem));
   return run_batched(w, out, batch, sizeof(T) * (size_t)(J + 1) * n, sizeof(T) * n, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
+                       if (fast) {
+                         const int rc = imodwt_fast<T>(di, nb, n, taps, J, dout, st);
+                         if (rc != WTB_EUNSUPPORTED) return rc;
+                         WTB_TRY(set_smem(kern, smem));
+                       }
                        kern<<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, n, J, taps, (T *)dout);
                        WTB_LAUNCH_CHECK();
                        return WTB_OK;
@@ -399,6 +303,54 @@ static int mra_impl(const void *w, int64_t batch, int n, const double *filt, int
   });
 }
 
+// Periodised equivalent filters [h_1 .. h_J, g_J] of the reference's modwtmra
+// (src/modwt.py:56-83, 172-193) from the UNSCALED taps g = dec_lo, h = dec_hi.
+static void equivalent_filters(const double *g, const double *h, int L, int J, int n, std::vector<double> *filt) {
+  auto dilate = [&](const double *taps, int j) {  // upArrow_op: 2^(j-1)-1 zeros between taps; j == 0 -> [1]
+    if (j == 0) return std::vector<double>{1.0};
+    const size_t step = size_t(1) << (j - 1);
+    std::vector<double> out(step * (L - 1) + 1, 0.0);
+    for (int l = 0; l < L; ++l) out[step * l] = taps[l];
+    return out;
+  };
+  auto conv = [](const std::vector<double> &a, const std::vector<double> &b) {
+    std::vector<double> out(a.size() + b.size() - 1, 0.0);
+    for (size_t i = 0; i < a.size(); ++i)
+      for (size_t k = 0; k < b.size(); ++k) out[i + k] += a[i] * b[k];
+    return out;
+  };
+  filt->assign((size_t)(J + 1) * n, 0.0);
+  auto fold = [&](const std::vector<double> &f, double scale, int row) {  // period_list
+    for (size_t i = 0; i < f.size(); ++i) (*filt)[(size_t)row * n + i % n] += f[i] * scale;
+  };
+  std::vector<double> g_part{1.0};
+  for (int j = 0; j < J; ++j) {
+    g_part = conv(g_part, dilate(g, j));
+    if (j == 0)
+      fold(std::vector<double>(h, h + L), 1.0 / std::sqrt(2.0), 0);
+    else
+      fold(conv(g_part, dilate(h, j + 1)), std::pow(2.0, -(j + 1) / 2.0), j);
+  }
+  fold(conv(g_part, dilate(g, J)), std::pow(2.0, -J / 2.0), J);
+}
+
+template <typename T>
+static int mra_taps_impl(const void *w, int64_t batch, int n, const Taps &taps, const double *g, const double *h,
+                         int J, int flags, void *out, cudaStream_t st) {
+  const size_t row = sizeof(T) * (size_t)(J + 1) * n;
+  bool covered = !(flags & WTB_GENERIC_ONLY) && fast_taps_ok(taps.L);
+  if (covered) {
+    int rc = run_batched(w, out, batch, row, row, flags, st, [&](const void *di, void *dout, int64_t nb) -> int {
+      return mra_fast<T>(di, nb, n, taps, J, dout, st);
+    });
+    if (rc != WTB_EUNSUPPORTED) return rc;
+  }
+  // shape outside the cascade kernel: correlate with the host-built periodised filters
+  std::vector<double> filt;
+  equivalent_filters(g, h, taps.L, J, n, &filt);
+  return mra_impl<T>(w, batch, n, filt.data(), J, flags, out, st);
+}
+
 static int make_plan(int n, int L, int level, const int *lens_in, LevelPlan *p) {
   WTB_REQUIRE(level >= 0 && level <= kMaxLevels, WTB_EUNSUPPORTED, "level %d outside [0,%d]", level, kMaxLevels);
   p->level = level;
@@ -425,9 +377,15 @@ static int wavedec_impl(const void *x, int64_t batch, int n, const Taps &taps, i
   WTB_TRY(make_plan(n, taps.L, level, nullptr, &plan));
   plan.buf = (n + 3) & ~3;
   const size_t smem = sizeof(T) * 2 * (size_t)plan.buf;
-  WTB_TRY(set_smem(k_wavedec<T>, smem));
+  const bool fast = !(flags & WTB_GENERIC_ONLY) && fast_taps_ok(taps.L);
+  if (!fast) WTB_TRY(set_smem(k_wavedec<T>, smem));
   return run_batched(x, coeffs, batch, sizeof(T) * n, sizeof(T) * (size_t)plan.total, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
+                       if (fast) {
+                         const int rc = wavedec_fast<T>(di, nb, plan, taps, dout, st);
+                         if (rc != WTB_EUNSUPPORTED) return rc;
+                         WTB_TRY(set_smem(k_wavedec<T>, smem));
+                       }
                        k_wavedec<T><<<(unsigned)nb, threads_for(n), smem, st>>>((const T *)di, plan, taps, (T *)dout);
                        WTB_LAUNCH_CHECK();
                        return WTB_OK;
@@ -445,9 +403,15 @@ static int waverec_impl(const void *coeffs, int64_t batch, const int *lens, int 
   for (int i = 0; i <= level; ++i) longest = std::max(longest, plan.len[i]);
   plan.buf = (longest + taps.L + 3) & ~3;
   const size_t smem = sizeof(T) * 2 * (size_t)plan.buf;
-  WTB_TRY(set_smem(k_waverec<T>, smem));
+  const bool fast = !(flags & WTB_GENERIC_ONLY) && fast_taps_ok(taps.L);
+  if (!fast) WTB_TRY(set_smem(k_waverec<T>, smem));
   return run_batched(coeffs, x, batch, sizeof(T) * (size_t)plan.total, sizeof(T) * (size_t)nout, flags, st,
                      [&](const void *di, void *dout, int64_t nb) -> int {
+                       if (fast) {
+                         const int rc = waverec_fast<T>(di, nb, plan, taps, dout, st);
+                         if (rc != WTB_EUNSUPPORTED) return rc;
+                         WTB_TRY(set_smem(k_waverec<T>, smem));
+                       }
                        k_waverec<T><<<(unsigned)nb, threads_for(nout), smem, st>>>((const T *)di, plan, taps, (T *)dout);
                        WTB_LAUNCH_CHECK();
                        return WTB_OK;
@@ -486,6 +450,16 @@ extern "C" int wtb_modwtmra(const void *w, int64_t batch, int n, const double *f
   WTB_TRY(ensure_device());
   if (batch == 0) return WTB_OK;
   return DISPATCH(mra_impl, w, batch, n, filt, J, flags, out, (cudaStream_t)stream);
+}
+
+extern "C" int wtb_modwtmra_taps(const void *w, int64_t batch, int n, const double *g, const double *h, int L,
+                                 int J, int flags, void *out, void *stream) {
+  WTB_REQUIRE(w && out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_modwtmra_taps: bad arguments");
+  Taps taps;
+  WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  return DISPATCH(mra_taps_impl, w, batch, n, taps, g, h, J, flags, out, (cudaStream_t)stream);
 }
 
 extern "C" int wtb_wavedec(const void *x, int64_t batch, int n, const double *dec_lo, const double *dec_hi,

@@ -20,12 +20,17 @@ __all__ = ["Wavelet", "wavedec", "waverec", "dwt", "idwt", "dwt_max_level", "wav
 _SCALING = {
     "haar": (0.7071067811865476, 0.7071067811865476),
     "db2": (-0.12940952255126037, 0.2241438680420134, 0.8365163037378079, 0.48296291314453416),
+    "db3": (0.035226291882100656, -0.08544127388224149, -0.13501102001039084, 0.4598775021193313,
+            0.8068915093133388, 0.3326705529509569),
+    "db5": (0.003335725285001549, -0.012580751999015526, -0.006241490213011705, 0.07757149384006515,
+            -0.03224486958502952, -0.24229488706619015, 0.13842814590110342, 0.7243085284385744,
+            0.6038292697974729, 0.160102397974125),
     "db4": (-0.010597401784997278, 0.032883011666982945, 0.030841381835986965, -0.18703481171888114,
             -0.02798376941698385, 0.6308807679295904, 0.7148465705525415, 0.23037781330885523),
     "sym4": (-0.07576571478927333, -0.02963552764599851, 0.49761866763201545, 0.8037387518059161,
              0.29785779560527736, -0.09921954357684722, -0.012603967262037833, 0.0322231006040427),
 }
-_ALIASES = {"db1": "haar", "la8": "sym4", "sym2": "db2"}
+_ALIASES = {"db1": "haar", "la8": "sym4", "sym2": "db2", "sym3": "db3"}
 
 
 def wavelist():

@@ -93,27 +93,68 @@ struct Chain {
 // wrap-around halo (elements) a level with dilation 2^sh reads on one side, TMA-sized
 __host__ __device__ __forceinline__ int halo_of(int L, int sh) { return (((L - 1) << sh) + 3) & ~3; }
 
-// Stage row[0..n) plus a copy of its first `head` / last `tail` elements after / before it.
-// head / tail are multiples of 4 elements; the TMA path needs 16-byte aligned rows.
-// `rows` loads of the same shape share one arrival on `bar`: the first call passes rows > 0 and
-// arms the barrier for all of them, later calls for the same phase pass rows = 0.
-template <typename T>
-__device__ __forceinline__ void issue_row_tma(T *dst, const T *src, int n, int head, int tail, uint64_t *bar,
-                                              int rows = 1) {
-  const uint32_t s = sizeof(T);
-  if (rows) mbar_expect_tx(bar, s * (uint32_t)(n + head + tail) * rows);
-  tma_load_1d(dst, src, s * n, bar);
-  if (head) tma_load_1d(dst + n, src, s * head, bar);
-  if (tail) tma_load_1d(dst - tail, src + n - tail, s * tail, bar);
+// ---- rows at any element alignment --------------------------------------------------------
+// A 1-D bulk copy needs 16-byte aligned addresses and sizes, but rows of an odd-length batch
+// start 4, 8 or 12 bytes off.  The copy therefore covers the enclosing 16-byte aligned span
+// (at most 15 bytes of the neighbouring rows on either side) and the row is addressed `shift`
+// elements into its shared-memory slot; every shared-memory access of the kernels is scalar,
+// so the slot's own alignment does not matter.  Stores mirror this: the row is staged at the
+// shift of its global address, the aligned body leaves by TMA and the <= 3 elements on each
+// end by plain stores.
+template <typename T> __device__ __forceinline__ int shift_of(const T *p) {
+  return (int)((reinterpret_cast<uintptr_t>(p) & 15) / sizeof(T));
 }
-template <typename T>
-__device__ __forceinline__ void copy_row_coop(T *dst, const T *__restrict__ src, int n, int head, int tail) {
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const T val = src[t];
-    dst[t] = val;
-    if (t < head) dst[n + t] = val;
-    if (t >= n - tail) dst[t - n] = val;
+
+template <typename T> struct RowIn {
+  const T *src;
+  int n, shift;
+  bool aligned;  // no shift and a whole number of 16-byte units: halos can come by TMA too
+  __device__ __forceinline__ RowIn(const T *src_, int n_) : src(src_), n(n_) {
+    shift = shift_of(src);
+    aligned = shift == 0 && (sizeof(T) * (size_t)n) % 16 == 0;
   }
+  // thread 0.  slot: 16-byte aligned, room for tail + 4 + n + head elements around slot[0].
+  // head / tail (multiples of 4): copies of the first / last elements after / before the row.
+  __device__ __forceinline__ void issue(T *slot, int head, int tail, uint64_t *bar) const {
+    const uint32_t s = sizeof(T);
+    if (aligned) {
+      mbar_expect_tx(bar, s * (uint32_t)(n + head + tail));
+      tma_load_1d(slot, src, s * n, bar);
+      if (head) tma_load_1d(slot + n, src, s * head, bar);
+      if (tail) tma_load_1d(slot - tail, src + n - tail, s * tail, bar);
+    } else {
+      const uint32_t bytes = (uint32_t)((s * (size_t)(shift + n) + 15) & ~size_t(15));
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(slot, src - shift, bytes, bar);
+    }
+  }
+  // all threads, after the barrier wait; returns the row pointer.  Unaligned rows build their
+  // halos here (one extra CTA barrier).
+  __device__ __forceinline__ T *finish(T *slot, int head, int tail) const {
+    T *row = slot + shift;
+    if (!aligned) {
+      for (int k = threadIdx.x; k < head; k += blockDim.x) row[n + k] = row[k];
+      for (int k = threadIdx.x; k < tail; k += blockDim.x) row[-1 - k] = row[n - 1 - k];
+      __syncthreads();
+    }
+    return row;
+  }
+};
+
+// All threads, after the barrier that published `row` (staged at shift_of(dst) in a 16-byte
+// aligned slot) and a fence_smem_to_async().  Thread 0 owns the bulk group.
+template <typename T>
+__device__ __forceinline__ void store_row(T *dst, const T *row, int n) {
+  const int per16 = 16 / (int)sizeof(T);
+  const int head = min(n, (per16 - shift_of(dst)) & (per16 - 1));
+  const int body = (n - head) & ~(per16 - 1);
+  if (threadIdx.x == 0 && body) {
+    tma_store_1d(dst + head, row + head, (uint32_t)(sizeof(T) * (size_t)body));
+    tma_store_commit();
+  }
+  const int k = threadIdx.x;
+  if (k < head) dst[k] = row[k];
+  if (k < per16 && head + body + k < n) dst[head + body + k] = row[head + body + k];
 }
 
 // ---- MODWT analysis: w_j[t] = sum_l h[l] v[(t - d l) mod n], v_j with g ------------------
@@ -158,62 +199,49 @@ __device__ __forceinline__ void analysis_level(T *__restrict__ v, T *__restrict_
 }
 
 template <typename T, int L>
-__global__ void __launch_bounds__(kChainThreads, 2) k_modwt_blk(const T *__restrict__ x, int n, int J, TapsK<T, L> tp, T *__restrict__ out) {
+__global__ void __launch_bounds__(kChainThreads, 2) k_modwt_blk(const T *__restrict__ x, int n, int J, TapsK<T, L> tp,
+                                                                T *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  const int HL = halo_of(L, J - 1);                       // left halo of the deepest level
-  const int np = (n + (kRM - 1) * (1 << (J - 1)) + 3) & ~3;  // + window tail of discarded chain slots
-  T *v = reinterpret_cast<T *>(smem_raw) + HL;
-  T *wb = v + np;
+  const int HL = halo_of(L, J - 1);                              // left halo of the deepest level
+  const int np = (n + (kRM - 1) * (1 << (J - 1)) + 4 + 3) & ~3;  // + discarded chain slots + shift
+  T *v_slot = reinterpret_cast<T *>(smem_raw) + HL;
+  T *w_slot = v_slot + np;
   const int64_t b = blockIdx.x;
-  const T *xr = x + b * n;
+  const RowIn<T> rin(x + b * n, n);
   T *o = out + b * (int64_t)(J + 1) * n;
-  const uint32_t bytes = (uint32_t)(sizeof(T) * (size_t)n);
-  const bool tma_in = tma_row_ok(xr, bytes), tma_out = tma_row_ok(o, bytes);
   const int h0 = halo_of(L, 0);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_init_fence();
   }
   __syncthreads();
-  if (tma_in) {
-    if (threadIdx.x == 0) issue_row_tma(v, xr, n, 0, h0, &bar);
-    mbar_wait(&bar, 0);
-  } else {
-    copy_row_coop(v, xr, n, 0, h0);
-    __syncthreads();
-  }
+  if (threadIdx.x == 0) rin.issue(v_slot, 0, h0, &bar);
+  mbar_wait(&bar, 0);
+  T *v = rin.finish(v_slot, 0, h0);
   for (int j = 1; j <= J; ++j) {
     const int mirror = j < J ? halo_of(L, j) : 0;
+    T *orow = o + (int64_t)(j - 1) * n;
+    T *wb = w_slot + shift_of(orow);
     const Chain ch(n, j - 1, kRM);
     switch (j - 1) {
 #define WTB_LEVEL(SH) \
-  case SH: analysis_level<T, L, SH>(v, wb, n, mirror, tp, tma_out, ch); break;
+  case SH: analysis_level<T, L, SH>(v, wb, n, mirror, tp, true, ch); break;
       WTB_LEVEL(0) WTB_LEVEL(1) WTB_LEVEL(2) WTB_LEVEL(3) WTB_LEVEL(4)
       WTB_LEVEL(5) WTB_LEVEL(6) WTB_LEVEL(7) WTB_LEVEL(8) WTB_LEVEL(9)
 #undef WTB_LEVEL
     }
-    if (tma_out) fence_smem_to_async();
+    fence_smem_to_async();
     __syncthreads();
-    T *orow = o + (int64_t)(j - 1) * n;
-    if (tma_out) {
-      if (threadIdx.x == 0) {
-        tma_store_1d(orow, wb, bytes);
-        tma_store_commit();
-      }
-    } else {
-      for (int t = threadIdx.x; t < n; t += blockDim.x) orow[t] = wb[t];
-    }
+    store_row(orow, wb, n);
   }
-  if (tma_out) {
-    if (threadIdx.x == 0) {
-      tma_store_1d(o + (int64_t)J * n, v, bytes);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
+  T *vrow = o + (int64_t)J * n;
+  if (shift_of(vrow) == rin.shift) {
+    store_row(vrow, v, n);
   } else {
-    for (int t = threadIdx.x; t < n; t += blockDim.x) o[(int64_t)J * n + t] = v[t];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) vrow[t] = v[t];
   }
+  if (threadIdx.x == 0) tma_store_wait_all();
 }
 
 // Write a chain in place; samples t < mirror are repeated at t + n (the right halo the next,
@@ -270,44 +298,39 @@ __device__ __forceinline__ void synthesis_level(const T *__restrict__ wj, T *__r
 }
 
 template <typename T, int L>
-__global__ void __launch_bounds__(kChainThreads, 2) k_imodwt_blk(const T *__restrict__ w, int n, int J, TapsK<T, L> tp, T *__restrict__ out) {
+__global__ void __launch_bounds__(kChainThreads, 2) k_imodwt_blk(const T *__restrict__ w, int n, int J, TapsK<T, L> tp,
+                                                                 T *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar[2];
-  // row + wrap halo + window tail of discarded chain slots
-  const int np = (n + (kRM + L - 2) * (1 << (J - 1)) + 3) & ~3;
-  T *v = reinterpret_cast<T *>(smem_raw);
-  T *wjb = v + np;  // [2][np]: w_j rows, the next one prefetched while this one is used
+  __shared__ __align__(8) uint64_t bar[3];  // w rows alternate on [0], [1]; v_J arrives on [2]
+  // row + wrap halo + window tail of discarded chain slots + alignment shift
+  const int np = (n + (kRM + L - 2) * (1 << (J - 1)) + 4 + 3) & ~3;
+  T *v_slot = reinterpret_cast<T *>(smem_raw);
+  T *w_slot = v_slot + np;  // [2][np]: w_j rows, the next one prefetched while this one is used
   const int64_t b = blockIdx.x;
   const T *wb = w + b * (int64_t)(J + 1) * n;
-  const uint32_t bytes = (uint32_t)(sizeof(T) * (size_t)n);
-  const bool tma_in = tma_row_ok(wb, bytes);
-  const bool tma_out = tma_row_ok(out + b * n, bytes);
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
     mbar_init_fence();
   }
   __syncthreads();
   const int hJ = halo_of(L, J - 1);
-  if (tma_in) {
-    if (threadIdx.x == 0) {
-      issue_row_tma(v, wb + (int64_t)J * n, n, hJ, 0, &bar[0], 2);  // one arrival covers both rows
-      issue_row_tma(wjb, wb + (int64_t)(J - 1) * n, n, hJ, 0, &bar[0], 0);
-    }
-  } else {
-    copy_row_coop(v, wb + (int64_t)J * n, n, hJ, 0);
-    copy_row_coop(wjb, wb + (int64_t)(J - 1) * n, n, hJ, 0);
-    __syncthreads();
+  const RowIn<T> rv(wb + (int64_t)J * n, n);
+  if (threadIdx.x == 0) {
+    rv.issue(v_slot, hJ, 0, &bar[2]);
+    RowIn<T>(wb + (int64_t)(J - 1) * n, n).issue(w_slot, hJ, 0, &bar[0]);
   }
+  mbar_wait(&bar[2], 0);
+  T *v = rv.finish(v_slot, hJ, 0);
   for (int j = J; j >= 1; --j) {
     const int it = J - j, cur = it & 1;
-    const T *wj = wjb + cur * np;
-    T *wnext = wjb + (cur ^ 1) * np;  // last read in iteration it-1, which ended with a barrier
-    if (tma_in) {
-      if (threadIdx.x == 0 && j > 1)
-        issue_row_tma(wnext, wb + (int64_t)(j - 2) * n, n, halo_of(L, j - 2), 0, &bar[cur ^ 1]);
-      mbar_wait(&bar[cur], (it >> 1) & 1);
-    }
+    const RowIn<T> rw(wb + (int64_t)(j - 1) * n, n);
+    // the other slot was last read in iteration it-1, which ended with a barrier
+    if (threadIdx.x == 0 && j > 1)
+      RowIn<T>(wb + (int64_t)(j - 2) * n, n).issue(w_slot + (cur ^ 1) * np, halo_of(L, j - 2), 0, &bar[cur ^ 1]);
+    mbar_wait(&bar[cur], (it >> 1) & 1);
+    const T *wj = rw.finish(w_slot + cur * np, halo_of(L, j - 1), 0);
     const int mirror = j > 1 ? halo_of(L, j - 2) : 0;
     const Chain ch(n, j - 1, kRM);
     switch (j - 1) {
@@ -317,18 +340,15 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_imodwt_blk(const T *__rest
       WTB_LEVEL(5) WTB_LEVEL(6) WTB_LEVEL(7) WTB_LEVEL(8) WTB_LEVEL(9)
 #undef WTB_LEVEL
     }
-    if (!tma_in && j > 1) copy_row_coop(wnext, wb + (int64_t)(j - 2) * n, n, halo_of(L, j - 2), 0);
     if (j == 1) fence_smem_to_async();
     __syncthreads();
   }
-  if (tma_out) {
-    if (threadIdx.x == 0) {
-      tma_store_1d(out + b * n, v, bytes);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
+  T *xrow = out + b * n;
+  if (shift_of(xrow) == rv.shift) {
+    store_row(xrow, v, n);
+    if (threadIdx.x == 0) tma_store_wait_all();
   } else {
-    for (int t = threadIdx.x; t < n; t += blockDim.x) out[b * n + t] = v[t];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) xrow[t] = v[t];
   }
 }
 
@@ -364,23 +384,19 @@ template <typename T, int L>
 __global__ void __launch_bounds__(kChainThreads, 2) k_mra_blk(const T *__restrict__ w, int n, int J, TapsK<T, L> tp, T *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  T *a = reinterpret_cast<T *>(smem_raw);
+  T *a_slot = reinterpret_cast<T *>(smem_raw);
   const int row = blockIdx.x % (J + 1);
   const int64_t off = (int64_t)blockIdx.x * n;  // (b (J+1) + row) n
   const int lev = row < J ? row + 1 : J;
-  const uint32_t bytes = (uint32_t)(sizeof(T) * (size_t)n);
+  const RowIn<T> rin(w + off, n);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_init_fence();
   }
   __syncthreads();
-  if (tma_row_ok(w + off, bytes)) {
-    if (threadIdx.x == 0) issue_row_tma(a, w + off, n, halo_of(L, lev - 1), 0, &bar);
-    mbar_wait(&bar, 0);
-  } else {
-    copy_row_coop(a, w + off, n, halo_of(L, lev - 1), 0);
-    __syncthreads();
-  }
+  if (threadIdx.x == 0) rin.issue(a_slot, halo_of(L, lev - 1), 0, &bar);
+  mbar_wait(&bar, 0);
+  T *a = rin.finish(a_slot, halo_of(L, lev - 1), 0);
   for (int k = lev; k >= 1; --k) {
     const int mirror = k > 1 ? halo_of(L, k - 2) : 0;
     const bool first = k == lev && row < J;  // the detail rows enter through the wavelet filter
@@ -400,12 +416,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_mra_blk(const T *__restric
     if (k == 1) fence_smem_to_async();
     __syncthreads();
   }
-  if (tma_row_ok(out + off, bytes)) {
-    if (threadIdx.x == 0) {
-      tma_store_1d(out + off, a, bytes);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
+  if (shift_of(out + off) == rin.shift) {
+    store_row(out + off, a, n);
+    if (threadIdx.x == 0) tma_store_wait_all();
   } else {
     for (int t = threadIdx.x; t < n; t += blockDim.x) out[off + t] = a[t];
   }
@@ -423,16 +436,20 @@ __global__ void k_wavedec_blk(const T *__restrict__ x, LevelPlan plan, TapsK<T, 
   constexpr int R = kRD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  T *a = reinterpret_cast<T *>(smem_raw) + kHalo;      // a[-kHalo .. plan.buf - kHalo)
-  T *pk = reinterpret_cast<T *>(smem_raw) + plan.buf;  // the packed output row cA_L | cD_L | .. | cD_1
   const int64_t b = blockIdx.x;
+  T *o = coeffs + b * (int64_t)plan.total;
+  const RowIn<T> rin(x + b * (int64_t)plan.n, plan.n);
+  T *a_slot = reinterpret_cast<T *>(smem_raw) + kHalo;  // signal slot: [-kHalo .. plan.buf - kHalo)
+  // the packed output row cA_L | cD_L | .. | cD_1, staged at the alignment of its global row
+  T *pk = reinterpret_cast<T *>(smem_raw) + plan.buf + shift_of(o);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_init_fence();
   }
   __syncthreads();
-  uint32_t phase = 0;
-  stage_row<T>(a, x + b * (int64_t)plan.n, plan.n, &bar, phase);
+  if (threadIdx.x == 0) rin.issue(a_slot, 0, 0, &bar);
+  mbar_wait(&bar, 0);
+  T *a = a_slot + rin.shift;
   int cur = plan.n;
   if ((int)threadIdx.x < L - 1) {
     const int k = threadIdx.x;
@@ -484,17 +501,8 @@ __global__ void k_wavedec_blk(const T *__restrict__ x, LevelPlan plan, TapsK<T, 
     fence_smem_to_async();
     __syncthreads();
   }
-  T *o = coeffs + b * (int64_t)plan.total;
-  const uint32_t bytes = (uint32_t)(sizeof(T) * (size_t)plan.total);
-  if (tma_row_ok(o, bytes)) {
-    if (threadIdx.x == 0) {
-      tma_store_1d(o, pk, bytes);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
-  } else {
-    for (int i = threadIdx.x; i < plan.total; i += blockDim.x) o[i] = pk[i];
-  }
+  store_row(o, pk, plan.total);
+  if (threadIdx.x == 0) tma_store_wait_all();
 }
 
 // ---- DWT synthesis (pywt.waverec): full[p] = sum_k lo[p-2k] a[k] + hi[p-2k] d[k], kept
@@ -505,17 +513,22 @@ __global__ void k_waverec_blk(const T *__restrict__ coeffs, LevelPlan plan, Taps
   constexpr int R = kRD, H = L / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  T *a = reinterpret_cast<T *>(smem_raw);
-  T *an = a + plan.buf;
-  T *pk = an + plan.buf;
   const int64_t b = blockIdx.x;
+  T *o = x + b * (int64_t)plan.n;
+  const RowIn<T> rin(coeffs + b * (int64_t)plan.total, plan.total);
+  // ping-pong buffers staged at the alignment of the output row (an even shift: pair stores)
+  const int so = shift_of(o) & ~1;
+  T *a = reinterpret_cast<T *>(smem_raw) + so;
+  T *an = a + plan.buf;
+  T *pk_slot = reinterpret_cast<T *>(smem_raw) + 2 * plan.buf;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_init_fence();
   }
   __syncthreads();
-  uint32_t phase = 0;
-  stage_row<T>(pk, coeffs + b * (int64_t)plan.total, plan.total, &bar, phase);
+  if (threadIdx.x == 0) rin.issue(pk_slot, 0, 0, &bar);
+  mbar_wait(&bar, 0);
+  const T *pk = pk_slot + rin.shift;
   const T *ap = pk;  // cA_L sits at the head of the packed row
   int cur = plan.len[0];
   for (int slot = 1; slot <= plan.level; ++slot) {
@@ -551,14 +564,9 @@ __global__ void k_waverec_blk(const T *__restrict__ coeffs, LevelPlan plan, Taps
     an = (an == a) ? a + plan.buf : a;
     cur = 2 * npairs;
   }
-  T *o = x + b * (int64_t)plan.n;
-  const uint32_t bytes = (uint32_t)(sizeof(T) * (size_t)plan.n);
-  if (plan.level > 0 && tma_row_ok(o, bytes)) {
-    if (threadIdx.x == 0) {
-      tma_store_1d(o, const_cast<T *>(ap), bytes);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
+  if (plan.level > 0 && so == shift_of(o)) {
+    store_row(o, ap, plan.n);
+    if (threadIdx.x == 0) tma_store_wait_all();
   } else {
     for (int i = threadIdx.x; i < cur; i += blockDim.x) o[i] = ap[i];
   }
@@ -597,8 +605,8 @@ int modwt_fast(const void *x, int64_t batch, int n, const Taps &taps, int J, voi
   if (!fast_taps_ok(taps.L)) return WTB_EUNSUPPORTED;
   const int threads = chain_threads(n, taps.L, J);
   if (!threads) return WTB_EUNSUPPORTED;
-  const size_t v_len = (size_t)halo_of(taps.L, J - 1) + (size_t)((n + (kRM - 1) * (1 << (J - 1)) + 3) & ~3);
-  const size_t smem = sizeof(T) * (v_len + (size_t)((n + 3) & ~3));
+  const size_t v_len = (size_t)halo_of(taps.L, J - 1) + (size_t)((n + (kRM - 1) * (1 << (J - 1)) + 4 + 3) & ~3);
+  const size_t smem = sizeof(T) * (v_len + (size_t)((n + 4 + 3) & ~3));
   if (smem > kSmemLimit) return WTB_EUNSUPPORTED;
   WTB_TAPS_SWITCH(taps.L, {
     WTB_TRY(set_smem(k_modwt_blk<T, LT>, smem));
@@ -613,7 +621,7 @@ int imodwt_fast(const void *w, int64_t batch, int n, const Taps &taps, int J, vo
   if (!fast_taps_ok(taps.L)) return WTB_EUNSUPPORTED;
   const int threads = chain_threads(n, taps.L, J);
   if (!threads) return WTB_EUNSUPPORTED;
-  const size_t np = (size_t)((n + (kRM + taps.L - 2) * (1 << (J - 1)) + 3) & ~3);
+  const size_t np = (size_t)((n + (kRM + taps.L - 2) * (1 << (J - 1)) + 4 + 3) & ~3);
   const size_t smem = sizeof(T) * 3 * np;
   if (smem > kSmemLimit) return WTB_EUNSUPPORTED;
   WTB_TAPS_SWITCH(taps.L, {
@@ -629,7 +637,7 @@ int mra_fast(const void *w, int64_t batch, int n, const Taps &taps, int J, void 
   if (!fast_taps_ok(taps.L) || batch * (J + 1) >= (1LL << 31)) return WTB_EUNSUPPORTED;
   const int threads = chain_threads(n, taps.L, J);
   if (!threads) return WTB_EUNSUPPORTED;
-  const size_t smem = sizeof(T) * (size_t)((n + (kRM + taps.L - 2) * (1 << (J - 1)) + 3) & ~3);
+  const size_t smem = sizeof(T) * (size_t)((n + (kRM + taps.L - 2) * (1 << (J - 1)) + 4 + 3) & ~3);
   if (smem > kSmemLimit) return WTB_EUNSUPPORTED;
   WTB_TAPS_SWITCH(taps.L, {
     WTB_TRY(set_smem(k_mra_blk<T, LT>, smem));
@@ -653,8 +661,8 @@ int wavedec_fast(const void *x, int64_t batch, const LevelPlan &plan_in, const T
   }
   const int64_t items = ((plan.n + taps.L - 1) / 2 + kRD - 1) / kRD;
   if (items > 1024) return WTB_EUNSUPPORTED;
-  plan.buf = (kHalo + plan.n + taps.L + 2 * kRD + 3) & ~3;  // halo | signal | mirror + discarded-tail slack
-  const size_t smem = sizeof(T) * ((size_t)plan.buf + (size_t)((plan.total + 3) & ~3));
+  plan.buf = (kHalo + plan.n + taps.L + 2 * kRD + 4 + 3) & ~3;  // halo | shift | signal | mirror + discarded tail
+  const size_t smem = sizeof(T) * ((size_t)plan.buf + (size_t)((plan.total + 4 + 3) & ~3));
   if (smem > kSmemLimit) return WTB_EUNSUPPORTED;
   const int threads = round_threads(items);
   WTB_TAPS_SWITCH(taps.L, {
@@ -675,8 +683,8 @@ int waverec_fast(const void *coeffs, int64_t batch, const LevelPlan &plan_in, co
     longest = std::max(longest, plan.len[i]);
     if (i > 0 && plan.len[i] < taps.L / 2) return WTB_EUNSUPPORTED;  // no full output pair
   }
-  plan.buf = (longest + taps.L + 3) & ~3;
-  const size_t smem = sizeof(T) * (2 * (size_t)plan.buf + (size_t)((plan.total + 3) & ~3));
+  plan.buf = (longest + taps.L + 4 + 3) & ~3;
+  const size_t smem = sizeof(T) * (2 * (size_t)plan.buf + (size_t)((plan.total + 4 + 3) & ~3));
   if (smem > kSmemLimit) return WTB_EUNSUPPORTED;
   const int threads = round_threads((plan.n / 2 + kRD - 1) / kRD);
   WTB_TAPS_SWITCH(taps.L, {

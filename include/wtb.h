@@ -147,6 +147,17 @@ int wtb_waverec(const void *coeffs, int64_t batch, const int *lens, int level,
                 const double *rec_lo, const double *rec_hi, int L, int flags,
                 void *x_out, void *stream);
 
+/* ---- per-component regressions: replaces sm.OLS(output_j, add_constant(input_j)).fit()
+ * (src/regression.py:76-81,118-121, src/modwt.py:218-222) ------------------------------ */
+/* One simple regression y = a + b x per row.  x: [x_rows, n], y: [y_rows, n]; the row counts
+ * are equal, or one of them is 1 and that row is used for every regression (the reference's
+ * wavelet_approximation regresses ONE series on each smooth).  add_constant = 0 fits y = b x.
+ * stats_out: [rows, 8] doubles { nobs, intercept, slope, ssr, tss, sxx, mean_x, mean_y } with
+ * tss / sxx centred when add_constant (statsmodels' centered_tss), raw sums otherwise.
+ * Standard errors, t and p values follow on the host (api/regression.py). */
+int wtb_rowwise_ols(const void *x, int64_t x_rows, const void *y, int64_t y_rows, int n,
+                    int add_constant, int flags, double *stats_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

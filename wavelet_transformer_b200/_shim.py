@@ -75,6 +75,7 @@ _SIGNATURES = {
     "wtb_modwtmra_taps": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
     "wtb_dwt_coeff_lens": ([_i32, _i32, _i32, _pi], _i32),
     "wtb_dwt_max_level": ([_i32, _i32], _i32),
+    "wtb_rowwise_ols": ([_vp, _i64, _vp, _i64, _i32, _i32, _i32, _pd, _vp], _i32),
     "wtb_wavedec": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
     "wtb_waverec_len": ([_pi, _i32, _i32], _i32),
     "wtb_waverec": ([_vp, _i64, _pi, _i32, _pd, _pd, _i32, _i32, _vp, _vp], _i32),
@@ -217,6 +218,22 @@ def series_prep_device(x_ptr, batch, n, y_ptr, ar1_ptr, *, detrend=True, remove_
                                  DEVICE_PTRS | (F64 if f64 else 0), C.c_void_p(int(y_ptr)) if y_ptr else None,
                                  C.cast(C.c_void_p(int(ar1_ptr)), _pd) if ar1_ptr else None,
                                  C.c_void_p(int(stream))), "wtb_series_prep")
+
+
+def rowwise_ols(x, y, *, add_constant=True, f64=None):
+    """One simple regression per row (wtb_rowwise_ols).  x, y: [rows, n] or [n] (a single row is
+    broadcast against the other argument's rows).  Returns [rows, 8] float64 stats:
+    nobs, intercept, slope, ssr, tss, sxx, mean_x, mean_y."""
+    f64 = _resolve_f64(f64)
+    x2 = np.ascontiguousarray(np.atleast_2d(np.asarray(x)), dtype=_dtype(f64))
+    y2 = np.ascontiguousarray(np.atleast_2d(np.asarray(y)), dtype=_dtype(f64))
+    if x2.shape[1] != y2.shape[1]:
+        raise ValueError(f"x and y must have the same number of observations ({x2.shape[1]} != {y2.shape[1]})")
+    rows = max(x2.shape[0], y2.shape[0])
+    stats = np.empty((rows, 8))
+    _check(lib().wtb_rowwise_ols(_ptr(x2), x2.shape[0], _ptr(y2), y2.shape[0], x2.shape[1], int(bool(add_constant)),
+                                 F64 if f64 else 0, _dp(stats), None), "wtb_rowwise_ols")
+    return stats
 
 
 # ---------------------------------------------------------------- XWT / WCT

@@ -89,3 +89,10 @@ def smooth_signal(modwt_coeffs: npt.NDArray, mother_wavelet: str, levels: int):
     for i, l in enumerate(range(levels, 0, -1)):
         out[l]["signal"] = np.asarray(signals[i], dtype=float)
     return out
+
+
+def time_scale_regression(input_coeffs, output_coeffs, levels: int, add_constant: bool = True):
+    """Regress output on input for each component vector S_J, D_J, .., D_1 (modwt.py:197-229);
+    all ``levels + 1`` regressions run in one device launch."""
+    from .regression import time_scale_regression_components
+    return time_scale_regression_components(input_coeffs, output_coeffs, levels, add_constant)

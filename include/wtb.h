@@ -40,6 +40,11 @@ extern "C" {
 #define WTB_NOISE_WHITE  (1 << 3)  /* Monte Carlo surrogates: white instead of AR(1) */
 #define WTB_GENERIC_ONLY (1 << 4)  /* force the generic (any pow2 N) kernels; testing */
 
+/* mother wavelets of wtb_cwt / wtb_cwt_axes_mother (pycwt.mothers) */
+#define WTB_MORLET 0   /* param = f0 */
+#define WTB_PAUL   1   /* param = order m */
+#define WTB_DOG    2   /* param = derivative m (m = 2: Mexican hat) */
+
 #define WTB_NBINS 1000             /* pycwt wct_significance: nbins = 1000 */
 
 /* ---- runtime ------------------------------------------------------------ */
@@ -68,6 +73,21 @@ int wtb_cwt_axes(int n0, double dt, double dj, double s0, int J, double f0,
 int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft,
                    double dt, double dj, double s0, int J, double f0, int flags,
                    void *power_out, void *coef_out, void *stream);
+
+/* The same two calls for any pycwt mother wavelet (constants/results_configs.py:53-58 builds
+ * Paul and DOG objects next to Morlet): psi_ft is pi^-1/4 exp(-(sw-f0)^2/2) for Morlet,
+ * 2^m/sqrt(m (2m-1)!) (sw)^m exp(-sw) H(sw) for Paul, -i^m/sqrt(Gamma(m+1/2)) (sw)^m exp(-(sw)^2/2)
+ * for DOG; flambda = 4pi/(f0+sqrt(2+f0^2)), 4pi/(2m+1), 2pi/sqrt(m+1/2).  Morlet goes through the
+ * same code as wtb_cwt_morlet (including its fused FP32 kernel). */
+int wtb_cwt_axes_mother(int n0, double dt, double dj, double s0, int J, int mother, double param,
+                        int *J_out, double *scales, double *freqs, double *coi);
+int wtb_cwt(const void *x, int64_t batch, int n0, int nfft, double dt, double dj, double s0, int J,
+            int mother, double param, int flags, void *power_out, void *coef_out, void *stream);
+/* Inverse transform, replaces pycwt.icwt (Torrence & Compo eq. 11):
+ * x_out[b,t] = factor * sum_s Re(W[b,s,t]) / sqrt(scales[s]) with factor =
+ * dj sqrt(dt) / (C_delta psi_0(0)) formed by the caller.  coef: [batch, S, n0] complex. */
+int wtb_icwt(const void *coef, int64_t batch, int S, int n0, const double *scales, double factor,
+             int flags, void *x_out, void *stream);
 
 /* ---- batched pre-processing: replaces standardize_series (src/utils/wavelet_helpers.py:22-57)
  * and pycwt.ar1 (src/cwt.py:106) for batches of series ------------------------------------ */

@@ -71,6 +71,61 @@ class Morlet:
         return convolve2d(T, win[:, None], "same")
 
 
+class Paul:
+    """pycwt.mothers.Paul [RECALLED]: psi_ft(f) = 2^m / sqrt(m (2m-1)!) f^m exp(-f) H(f)
+    (Torrence & Compo 1998, table 1); no ``smooth``."""
+
+    name = "paul"
+
+    def __init__(self, m: int = 4):
+        self.m, self.dofmin = m, 2
+        self.cdelta, self.gamma, self.deltaj0 = (1.132, 1.17, 1.50) if m == 4 else (-1, -1, -1)
+
+    def psi_ft(self, f):
+        pos = np.where(f > 0, f, 0.0)
+        return 2 ** self.m / np.sqrt(self.m * math.factorial(2 * self.m - 1)) * pos ** self.m * np.exp(-pos) * (f > 0)
+
+    def psi0(self) -> float:
+        """psi_0(0) = 2^m i^m m! / sqrt(pi (2m)!), real for even m."""
+        return float(np.real(2 ** self.m * 1j ** self.m * math.factorial(self.m)
+                             / np.sqrt(np.pi * math.factorial(2 * self.m))))
+
+    def flambda(self) -> float:
+        return 4 * np.pi / (2 * self.m + 1)
+
+    def coi(self) -> float:
+        return np.sqrt(2)  # e-folding time of T&C table 1; pycwt's own value unverified
+
+
+class DOG:
+    """pycwt.mothers.DOG [RECALLED]: psi_ft(f) = -i^m / sqrt(Gamma(m+1/2)) f^m exp(-f^2/2)."""
+
+    name = "dog"
+
+    def __init__(self, m: int = 2):
+        self.m, self.dofmin = m, 1
+        self.cdelta, self.gamma, self.deltaj0 = {2: (3.541, 1.43, 1.40), 6: (1.966, 1.37, 0.97)}.get(m, (-1, -1, -1))
+
+    def psi_ft(self, f):
+        return -(1j ** self.m) / np.sqrt(math.gamma(self.m + 0.5)) * f ** self.m * np.exp(-0.5 * f ** 2)
+
+    def psi0(self) -> float:
+        from numpy.polynomial.hermite_e import hermeval
+        return float((-1) ** (self.m + 1) * hermeval(0.0, [0] * self.m + [1]) / np.sqrt(math.gamma(self.m + 0.5)))
+
+    def flambda(self) -> float:
+        return 2 * np.pi / np.sqrt(self.m + 0.5)
+
+    def coi(self) -> float:
+        return 1.0 / np.sqrt(2)
+
+
+def icwt(W, sj, dt, dj, wavelet):
+    """pycwt.icwt [RECALLED]: Torrence & Compo (1998) eq. 11."""
+    psi0 = np.pi ** -0.25 if isinstance(wavelet, Morlet) else wavelet.psi0()
+    return dj * np.sqrt(dt) / (wavelet.cdelta * psi0) * (np.real(W) / np.sqrt(sj)[:, None]).sum(axis=0)
+
+
 def rect(n: int, normalize: bool = False):
     """pycwt.helpers.rect: boxcar with half-weight end points (A.2)."""
     w = np.ones(n)

@@ -111,3 +111,47 @@ def test_cwt_rejects_bad_arguments(shim):
         shim.cwt_morlet(x, DT, -1.0, 2 * DT, -1)                 # dj <= 0
     with pytest.raises((ValueError, RuntimeError)):
         shim.cwt_morlet(np.zeros(20000), DT, 1 / 8, 2 * DT, -1, f64=True)  # beyond the smem FFT
+
+
+# ---- other pycwt mothers and the inverse transform -----------------------
+@pytest.mark.parametrize("mother", ["paul4", "paul3", "dog2", "dog3", "dog6"])
+def test_cwt_other_mothers_fp64_and_fp32(shim, series, mother):
+    """Paul / DOG daughters (real and imaginary prefactors -i^m) through the generic kernel."""
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    kind, m = mother[:-1], int(mother[-1])
+    ref_m = po.Paul(m) if kind == "paul" else po.DOG(m)
+    eng_m = wavelet.Paul(m) if kind == "paul" else wavelet.DOG(m)
+    x = series["expectation_value"]
+    x = (x - x.mean()) / x.std()
+    W_ref, sj_ref, fr_ref, coi_ref, _, _ = po.cwt(x, DT, 1 / 8, -1, -1, ref_m)
+    W, sj, fr, coi, _, _ = wavelet.cwt(x, DT, 1 / 8, -1, -1, eng_m)
+    assert W.shape == W_ref.shape and W.dtype == np.complex128
+    assert np.allclose(sj, sj_ref, rtol=1e-13) and np.allclose(fr, fr_ref, rtol=1e-13)
+    assert np.allclose(coi, coi_ref, rtol=1e-13)
+    assert np.abs(W - W_ref).max() <= 1e-10 * np.abs(W_ref).max()
+    code = shim.PAUL if kind == "paul" else shim.DOG
+    p32, _ = shim.cwt(x, DT, 1 / 8, -1, -1, code, m, f64=False)
+    ok, err = normwise_close(p32, np.abs(W_ref) ** 2, 1e-4)
+    assert ok, err
+
+
+def test_icwt_and_mother_names(shim, series):
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    x = series["inflation_value"]
+    x = (x - x.mean()) / x.std()
+    for name, ref_m in (("morlet", po.Morlet(6)), ("paul", po.Paul(4)), ("mexicanhat", po.DOG(2))):
+        W, sj, *_ = wavelet.cwt(x, DT, 1 / 12, -1, -1, name)
+        W_ref, sj_ref, *_ = po.cwt(x, DT, 1 / 12, -1, -1, ref_m)
+        assert np.abs(W - W_ref).max() <= 1e-10 * np.abs(W_ref).max()
+        rec = wavelet.icwt(W, sj, DT, 1 / 12, name)
+        rec_ref = po.icwt(W_ref, sj_ref, DT, 1 / 12, ref_m)
+        assert rec.shape == x.shape and np.abs(rec - rec_ref).max() <= 1e-10 * np.abs(rec_ref).max()
+        assert np.abs(wavelet.icwt(W.T, sj, DT, 1 / 12, name) - rec).max() == 0      # pycwt accepts the transpose
+    with pytest.raises(ValueError):
+        wavelet.cwt(x, DT, wavelet="haar")
+    with pytest.raises(NotImplementedError):
+        wavelet.wct(x, x[::-1].copy(), DT, sig=False, wavelet=wavelet.Paul(4))
+    batch = np.stack([np.asarray(wavelet.cwt(x * k, DT, 1 / 4, -1, -1, "dog")[0]) for k in (1.0, 2.0)])
+    sj4 = wavelet.cwt(x, DT, 1 / 4, -1, -1, "dog")[1]
+    out = shim.icwt(batch, sj4, 1.0, f64=True)                                       # batched entry point
+    assert np.allclose(out[1], 2 * out[0], rtol=1e-12)

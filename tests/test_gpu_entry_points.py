@@ -182,8 +182,10 @@ def test_pycwt_facade_cwt_side_outputs(series):
     assert W.dtype == np.complex128 and np.abs(W - Wo).max() <= 1e-10 * np.abs(Wo).max()
     assert np.allclose(sj, sjo) and np.allclose(fr, fro) and np.allclose(coi, coio)
     assert np.allclose(fft_, ffto) and np.allclose(fftfreqs, fqo)
+    Wp = wavelet.cwt(x, DT, 1 / 12, 2 * DT, 40, wavelet="paul")[0]      # other mothers: tests/test_gpu_cwt.py
+    assert np.abs(Wp - po.cwt(x, DT, 1 / 12, 2 * DT, 40, po.Paul(4))[0]).max() <= 1e-10 * np.abs(Wp).max()
     with pytest.raises(NotImplementedError):
-        wavelet.cwt(x, DT, wavelet="paul")
+        wavelet.xwt(x, x[::-1].copy(), DT, wavelet="paul")
 
 
 def test_series_prep_matches_reference_helpers(shim, series, helpers_golden):

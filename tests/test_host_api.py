@@ -153,3 +153,22 @@ def test_mra_filters_match_oracle():
             a = modwt.mra_filters(filt, 5, N)
             b = np.vstack(mo.mra_filters(filt, 5, N))
             assert np.array_equal(a, b)
+
+
+def test_significance_cache_files(tmp_path, monkeypatch):
+    """The on-disk significance cache: our exact-key file and, on request,
+    the file name pycwt itself would use (np.savetxt text, one float per line, gzip)."""
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    p = wavelet.pycwt_cache_file(0.1, -0.2, 1 / 12, 1 / 8, 1 / 6, 65, "morlet")
+    assert p.name == "wct_sig_0.00000_1.50000_0.12500_2.00000_65_Morlet.gz"   # arctanh(.4)->0, arctanh(-.8)->-1
+    q = wavelet.pycwt_cache_file(0.989, 0.966, 1 / 12, 1 / 8, 1 / 6, 65)
+    assert q.name == "wct_sig_nan_nan_0.12500_2.00000_65_Morlet.gz"           # pycwt's collision for |a| > 0.25
+    monkeypatch.setenv("WTB_PYCWT_CACHE_DIR", str(tmp_path / "pycwt"))
+    monkeypatch.setenv("WTB_CACHE_DIR", str(tmp_path / "own"))
+    monkeypatch.setenv("WTB_PYCWT_CACHE", "read")
+    sig = np.linspace(0.5, 0.9, 66)
+    target = wavelet.pycwt_cache_file(0.1, 0.2, 1 / 12, 1 / 8, 1 / 6, 65)
+    target.parent.mkdir(parents=True)
+    np.savetxt(target, sig)
+    got = wavelet.wct_significance(0.1, 0.2, dt=1 / 12, dj=1 / 8, s0=1 / 6, J=65)   # served from the file: no GPU call
+    assert np.allclose(got, sig)

@@ -111,3 +111,27 @@ def test_wct_significance_small_and_histogram_variants():
     a = po.coherence_histogram(R2, outside, maxscale, faithful_loop=True)
     b = po.coherence_histogram(R2, outside, maxscale, faithful_loop=False)
     assert np.array_equal(a, b)
+
+
+def test_other_mothers_known_answers():
+    """Torrence & Compo (1998) table 1 / table 2 constants for Paul (m=4) and DOG (m=2, 6):
+    psi_0(0), Fourier factors, unit energy of psi_ft, and the reconstruction identity
+    icwt(cwt(x)) ~ x that defines C_delta."""
+    assert po.Paul(4).psi0() == pytest.approx(1.079, abs=5e-4)
+    assert po.DOG(2).psi0() == pytest.approx(0.867, abs=5e-4)
+    assert po.DOG(6).psi0() == pytest.approx(0.884, abs=5e-4)
+    assert po.Paul(4).flambda() == pytest.approx(1.3963, abs=1e-4)
+    assert po.DOG(2).flambda() == pytest.approx(3.9738, abs=1e-4)
+    assert po.DOG(6).flambda() == pytest.approx(2.4645, abs=1e-4)
+    w = np.linspace(-40, 40, 400001)
+    for mother in (po.Paul(4), po.DOG(2), po.DOG(6), po.Morlet(6)):
+        assert np.trapezoid(np.abs(mother.psi_ft(w)) ** 2, w) == pytest.approx(1.0, rel=1e-6)
+    rng = np.random.default_rng(4)
+    t = np.arange(1024)
+    x = np.sin(2 * np.pi * t / 37.0) + 0.5 * np.sin(2 * np.pi * t / 90.0) + 0.1 * rng.standard_normal(1024)
+    x -= x.mean()
+    for mother, dj in ((po.Morlet(6), 1 / 16), (po.Paul(4), 1 / 16), (po.DOG(2), 1 / 16), (po.DOG(6), 1 / 16)):
+        W, sj, *_ = po.cwt(x, 1.0, dj, -1, -1, mother)
+        rec = po.icwt(W, sj, 1.0, dj, mother)
+        mid = slice(200, 824)
+        assert np.abs(rec[mid] - x[mid]).std() < 0.1 * x.std()

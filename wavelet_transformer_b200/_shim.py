@@ -62,6 +62,9 @@ _SIGNATURES = {
     "wtb_last_error": ([], C.c_char_p),
     "wtb_kernel_launches": ([], C.c_uint64),
     "wtb_cwt_axes": ([_i32, _f64, _f64, _f64, _i32, _f64, _pi, _pd, _pd, _pd], _i32),
+    "wtb_cwt_axes_mother": ([_i32, _f64, _f64, _f64, _i32, _i32, _f64, _pi, _pd, _pd, _pd], _i32),
+    "wtb_cwt": ([_vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _i32, _f64, _i32, _vp, _vp, _vp], _i32),
+    "wtb_icwt": ([_vp, _i64, _i32, _i32, _pd, _f64, _i32, _vp, _vp], _i32),
     "wtb_cwt_morlet": ([_vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp], _i32),
     "wtb_series_prep": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _pd, _vp], _i32),
     "wtb_xwt_wct": ([_vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp, _vp], _i32),
@@ -160,6 +163,57 @@ def cwt_axes(n0, dt, dj, s0=-1, J=-1, f0=6.0):
     _check(lib().wtb_cwt_axes(n0, dt, dj, s0, int(J), f0, C.byref(Jout), _dp(scales), _dp(freqs), _dp(coi)),
            "wtb_cwt_axes")
     return Jout.value, scales, freqs, coi
+
+
+MORLET, PAUL, DOG = 0, 1, 2  # WTB_MORLET / WTB_PAUL / WTB_DOG
+
+
+def cwt_axes_mother(n0, dt, dj, s0=-1, J=-1, mother=MORLET, param=6.0):
+    """cwt_axes for any mother wavelet (param = f0 for Morlet, the order m otherwise)."""
+    Jout = C.c_int(0)
+    _check(lib().wtb_cwt_axes_mother(n0, dt, dj, s0, int(J), int(mother), float(param), C.byref(Jout), None, None,
+                                     None), "wtb_cwt_axes_mother")
+    S = Jout.value + 1
+    scales, freqs, coi = np.empty(S), np.empty(S), np.empty(n0)
+    _check(lib().wtb_cwt_axes_mother(n0, dt, dj, s0, int(J), int(mother), float(param), C.byref(Jout), _dp(scales),
+                                     _dp(freqs), _dp(coi)), "wtb_cwt_axes_mother")
+    return Jout.value, scales, freqs, coi
+
+
+def cwt(x, dt, dj, s0, J, mother=MORLET, param=6.0, *, nfft=None, f64=None, want_power=True, want_coef=False,
+        coi_mask=False, generic_only=False):
+    """Batched CWT of host data with any mother wavelet (wtb_cwt); see cwt_morlet."""
+    f64 = _resolve_f64(f64)
+    rt = _dtype(f64)
+    x2 = np.ascontiguousarray(np.atleast_2d(np.asarray(x)), dtype=rt)
+    batch, n0 = x2.shape
+    Jr, _, _, _ = cwt_axes_mother(n0, dt, dj, s0, J, mother, param)
+    S = Jr + 1
+    nfft = int(nfft) if nfft else next_pow2(n0)
+    flags = (F64 if f64 else 0) | (COI_MASK if coi_mask else 0) | (GENERIC_ONLY if generic_only else 0)
+    power = np.empty((batch, S, n0), dtype=rt) if want_power else None
+    coef = np.empty((batch, S, n0), dtype=np.complex128 if f64 else np.complex64) if want_coef else None
+    _check(lib().wtb_cwt(_ptr(x2), batch, n0, nfft, dt, dj, s0, int(J), int(mother), float(param), flags,
+                         _ptr(power), _ptr(coef), None), "wtb_cwt")
+    if np.ndim(x) == 1:
+        power = power[0] if power is not None else None
+        coef = coef[0] if coef is not None else None
+    return power, coef
+
+
+def icwt(W, scales, factor, *, f64=None):
+    """factor * sum_s Re(W[s, t]) / sqrt(scales[s]) for W [S, n0] or [batch, S, n0] (wtb_icwt)."""
+    f64 = _resolve_f64(f64)
+    W = np.asarray(W)
+    w3 = np.ascontiguousarray(W[None] if W.ndim == 2 else W, dtype=np.complex128 if f64 else np.complex64)
+    batch, S, n0 = w3.shape
+    scales = np.ascontiguousarray(scales, dtype=np.float64)
+    if scales.shape != (S,):
+        raise ValueError("Input array dimensions do not match.")
+    out = np.empty((batch, n0), dtype=_dtype(f64))
+    _check(lib().wtb_icwt(_ptr(w3), batch, S, n0, _dp(scales), float(factor), F64 if f64 else 0, _ptr(out), None),
+           "wtb_icwt")
+    return out[0] if W.ndim == 2 else out
 
 
 def cwt_morlet(x, dt, dj, s0, J, f0=6.0, *, nfft=None, f64=None, want_power=True, want_coef=False,

@@ -95,10 +95,44 @@ inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 // Morlet constants (pycwt.mothers.Morlet)
 inline double morlet_flambda(double f0) { return 4.0 * kPi / (f0 + std::sqrt(2.0 + f0 * f0)); }
 
+// pycwt.mothers: kind = WTB_MORLET / WTB_PAUL / WTB_DOG, param = f0 or the order m
+struct Mother {
+  int kind = WTB_MORLET;
+  double param = 6.0;
+};
+inline double mother_flambda(const Mother &m) {
+  if (m.kind == WTB_PAUL) return 4.0 * kPi / (2.0 * m.param + 1.0);
+  if (m.kind == WTB_DOG) return 2.0 * kPi / std::sqrt(m.param + 0.5);
+  return morlet_flambda(m.param);
+}
+// e-folding factor of the cone of influence (Torrence & Compo table 1)
+inline double mother_coi(const Mother &m) { return m.kind == WTB_PAUL ? std::sqrt(2.0) : 1.0 / std::sqrt(2.0); }
+// conj of the constant complex prefactor of psi_ft (1 for Morlet: pi^-1/4 stays in the kernel)
+inline void mother_prefactor(const Mother &m, double *re, double *im) {
+  *re = 1.0;
+  *im = 0.0;
+  const int order = (int)m.param;
+  if (m.kind == WTB_PAUL) {
+    double fact = 1.0;  // (2m-1)!
+    for (int k = 2; k <= 2 * order - 1; ++k) fact *= k;
+    *re = std::pow(2.0, order) / std::sqrt(order * fact);
+  } else if (m.kind == WTB_DOG) {
+    const double c = 1.0 / std::sqrt(std::tgamma(m.param + 0.5));
+    // -i^m: m%4 = 0 -> -1, 1 -> -i, 2 -> +1, 3 -> +i; conjugated here
+    switch (order & 3) {
+      case 0: *re = -c; break;
+      case 1: *re = 0; *im = c; break;
+      case 2: *re = c; break;
+      default: *re = 0; *im = -c; break;
+    }
+  }
+}
+
 struct Axes {
   int J = 0;
   std::vector<double> scales, freqs;
 };
 int resolve_axes(int n0, double dt, double dj, double s0, int J, double f0, Axes *ax);
+int resolve_axes(int n0, double dt, double dj, double s0, int J, const Mother &m, Axes *ax);
 
 }  // namespace wtb

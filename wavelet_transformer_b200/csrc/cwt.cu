@@ -1,4 +1,4 @@
-// Batched Morlet CWT (pycwt.cwt, src/cwt.py:110-114 of the reference):
+// Batched CWT (pycwt.cwt, src/cwt.py:110-114 of the reference), Morlet unless stated:
 //   X = fft(x, nfft);  W[s,:] = ifft(X * sqrt(2*pi*s/dt) * pi^-1/4 * exp(-(s*w-f0)^2/2));
 //   power = |W|^2, truncated to the first n0 samples.
 // Generic kernels (any pow2 nfft, float/double) live here; the FP32 fast path
@@ -16,7 +16,8 @@ template <typename T>
 __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
                            int chunk, const double *__restrict__ scales, double dt, double f0,
                            const cplx<T> *__restrict__ tw, T *__restrict__ power,
-                           cplx<T> *__restrict__ coef, int coi_mask, double coi_c, double flambda) {
+                           cplx<T> *__restrict__ coef, int coi_mask, double coi_c, double flambda,
+                           int mother, int order, T pre_re, T pre_im) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T> *a = reinterpret_cast<cplx<T> *>(smem_raw);
   cplx<T> *b = a + N;
@@ -30,10 +31,25 @@ __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
     const T s_over_dt = T(sc / dt);
     // (s * ftfreqs[1] * N)^0.5 * pi^-0.25, times 1/N of the inverse transform
     const T norm = T(sqrt(2.0 * kPi * sc / dt) * kPiM14 / double(N));
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-      const T d = morlet_daughter<T>(k, N, s_over_dt, norm, T(f0));
-      cplx<T> v = xh[k];
-      a[k] = mk<T>(v.x * d, v.y * d);
+    if (mother == WTB_MORLET) {
+      for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const T d = morlet_daughter<T>(k, N, s_over_dt, norm, T(f0));
+        cplx<T> v = xh[k];
+        a[k] = mk<T>(v.x * d, v.y * d);
+      }
+    } else {
+      // Paul: (sw)^m exp(-sw) H(sw);  DOG: (sw)^m exp(-(sw)^2/2);  times conj(prefactor)
+      const T nrm = T(sqrt(2.0 * kPi * sc / dt) / double(N));
+      for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const int kk = (k < (N + 1) / 2) ? k : k - N;
+        const T z = s_over_dt * (T(2.0 * kPi) * T(kk) / T(N));
+        T zm = T(1);
+        for (int i = 0; i < order; ++i) zm *= z;
+        const T g = mother == WTB_PAUL ? (z > T(0) ? zm * dev_exp<T>(-z) : T(0)) : zm * dev_exp<T>(T(-0.5) * z * z);
+        const T dr = nrm * pre_re * g, di = nrm * pre_im * g;
+        cplx<T> v = xh[k];
+        a[k] = mk<T>(v.x * dr - v.y * di, v.x * di + v.y * dr);
+      }
     }
     __syncthreads();
     cplx<T> *r = block_fft<T, +1>(a, b, N, log2N, tw);
@@ -57,9 +73,11 @@ __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
 
 template <typename T>
 static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, const Axes &ax,
-                      double f0, int flags, T *d_power, cplx<T> *d_coef, cudaStream_t st) {
+                      const Mother &mo, int flags, T *d_power, cplx<T> *d_coef, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (sizeof(T) == 4 && d_coef == nullptr && d_power != nullptr && !(flags & WTB_GENERIC_ONLY)) {
+  const double f0 = mo.kind == WTB_MORLET ? mo.param : 0.0;
+  if (mo.kind == WTB_MORLET && sizeof(T) == 4 && d_coef == nullptr && d_power != nullptr &&
+      !(flags & WTB_GENERIC_ONLY)) {
     int rc = cwt_fast_try((const float *)d_x, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
     if (rc != 1) return rc;
   }
@@ -88,16 +106,19 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   chunk = std::max(1, std::min(chunk, 16));
   const int nchunks = (S + chunk - 1) / chunk;
   WTB_REQUIRE(batch * nchunks < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
+  double pre_re, pre_im;
+  mother_prefactor(mo, &pre_re, &pre_im);
   k_cwt_rows<T><<<(unsigned)(batch * nchunks), threads, smem, st>>>(
       d_xhat, n0, N, log2N, S, chunk, d_scales, dt, f0, tw, d_power, d_coef,
-      (flags & WTB_COI_MASK) ? 1 : 0, morlet_flambda(f0) / std::sqrt(2.0) * dt, morlet_flambda(f0));
+      (flags & WTB_COI_MASK) ? 1 : 0, mother_flambda(mo) * mother_coi(mo) * dt, mother_flambda(mo), mo.kind,
+      (int)mo.param, T(pre_re), T(pre_im));
   WTB_LAUNCH_CHECK();
   return WTB_OK;
 }
 
 template <typename T>
 static int cwt_entry(const void *x, int64_t batch, int n0, int N, double dt, const Axes &ax,
-                     double f0, int flags, void *power_out, void *coef_out, cudaStream_t st) {
+                     const Mother &f0, int flags, void *power_out, void *coef_out, cudaStream_t st) {
   const int S = ax.J + 1;
   if (flags & WTB_DEVICE_PTRS)
     return cwt_device<T>((const T *)x, batch, n0, N, dt, ax, f0, flags, (T *)power_out,
@@ -134,19 +155,85 @@ static int cwt_entry(const void *x, int64_t batch, int n0, int N, double dt, con
 
 using namespace wtb;
 
-extern "C" int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft, double dt, double dj,
-                              double s0, int J, double f0, int flags, void *power_out,
-                              void *coef_out, void *stream) {
-  WTB_REQUIRE(x && batch >= 0 && n0 > 0, WTB_EINVAL, "wtb_cwt_morlet: bad x/batch/n0");
-  WTB_REQUIRE(power_out || coef_out, WTB_EINVAL, "wtb_cwt_morlet: no output requested");
+extern "C" int wtb_cwt(const void *x, int64_t batch, int n0, int nfft, double dt, double dj, double s0, int J,
+                       int mother, double param, int flags, void *power_out, void *coef_out, void *stream) {
+  WTB_REQUIRE(x && batch >= 0 && n0 > 0, WTB_EINVAL, "wtb_cwt: bad x/batch/n0");
+  WTB_REQUIRE(power_out || coef_out, WTB_EINVAL, "wtb_cwt: no output requested");
   WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
               "nfft=%d must be a power of two >= n0=%d (pycwt's scipy.fftpack padding rule); "
               "the un-padded mkl_fft variant is not supported", nfft, n0);
   WTB_TRY(ensure_device());
+  Mother mo;
+  mo.kind = mother;
+  mo.param = param;
   Axes ax;
-  WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));
+  WTB_TRY(resolve_axes(n0, dt, dj, s0, J, mo, &ax));
   if (batch == 0) return WTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (flags & WTB_F64) return cwt_entry<double>(x, batch, n0, nfft, dt, ax, f0, flags, power_out, coef_out, st);
-  return cwt_entry<float>(x, batch, n0, nfft, dt, ax, f0, flags, power_out, coef_out, st);
+  if (flags & WTB_F64) return cwt_entry<double>(x, batch, n0, nfft, dt, ax, mo, flags, power_out, coef_out, st);
+  return cwt_entry<float>(x, batch, n0, nfft, dt, ax, mo, flags, power_out, coef_out, st);
+}
+
+extern "C" int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft, double dt, double dj,
+                              double s0, int J, double f0, int flags, void *power_out,
+                              void *coef_out, void *stream) {
+  return wtb_cwt(x, batch, n0, nfft, dt, dj, s0, J, WTB_MORLET, f0, flags, power_out, coef_out, stream);
+}
+
+// ---- inverse transform (pycwt.icwt): x[t] = factor * sum_s Re(W[s,t]) / sqrt(s_j) ----------
+namespace wtb {
+template <typename T>
+__global__ void k_icwt(const cplx<T> *__restrict__ coef, int S, int n0, const double *__restrict__ scales,
+                       double factor, T *__restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n0) return;
+  const cplx<T> *w = coef + b * (int64_t)S * n0 + t;
+  double acc = 0;
+  for (int s = 0; s < S; ++s) acc += (double)w[(int64_t)s * n0].x * rsqrt(scales[s]);
+  out[b * (int64_t)n0 + t] = T(factor * acc);
+}
+
+template <typename T>
+static int icwt_impl(const void *coef, int64_t batch, int S, int n0, const double *scales, double factor, int flags,
+                     void *out, cudaStream_t st) {
+  const bool dev = flags & WTB_DEVICE_PTRS;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  void *scratch = nullptr;
+  WTB_TRY(arena_reserve(al(sizeof(double) * S), &scratch));
+  double *d_scales = (double *)scratch;
+  WTB_CUDA(cudaMemcpyAsync(d_scales, scales, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+  const size_t in_row = sizeof(cplx<T>) * (size_t)S * n0, out_row = sizeof(T) * (size_t)n0;
+  const int64_t rows = dev ? batch : std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)((size_t(1) << 30) / in_row)));
+  const cplx<T> *d_in = (const cplx<T> *)coef;
+  T *d_out = (T *)out;
+  if (!dev) {
+    void *stage = nullptr;
+    WTB_TRY(staging_reserve(al(in_row * rows) + al(out_row * rows), &stage));
+    d_in = (const cplx<T> *)stage;
+    d_out = (T *)((char *)stage + al(in_row * rows));
+  }
+  for (int64_t b0 = 0; b0 < batch; b0 += rows) {
+    const int64_t nb = std::min(rows, batch - b0);
+    WTB_REQUIRE(nb < 65536, WTB_EUNSUPPORTED, "wtb_icwt: at most 65535 series per launch");
+    if (!dev) WTB_CUDA(cudaMemcpyAsync((void *)d_in, (const char *)coef + b0 * in_row, in_row * nb, cudaMemcpyHostToDevice, st));
+    k_icwt<T><<<dim3((n0 + 255) / 256, (unsigned)nb), 256, 0, st>>>(d_in, S, n0, d_scales, factor, d_out);
+    WTB_LAUNCH_CHECK();
+    if (!dev) {
+      WTB_CUDA(cudaMemcpyAsync((char *)out + b0 * out_row, d_out, out_row * nb, cudaMemcpyDeviceToHost, st));
+      WTB_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  return WTB_OK;
+}
+}  // namespace wtb
+
+extern "C" int wtb_icwt(const void *coef, int64_t batch, int S, int n0, const double *scales, double factor,
+                        int flags, void *x_out, void *stream) {
+  WTB_REQUIRE(coef && x_out && scales && batch >= 0 && S > 0 && n0 > 0, WTB_EINVAL, "wtb_icwt: bad arguments");
+  WTB_TRY(ensure_device());
+  if (batch == 0) return WTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & WTB_F64) return icwt_impl<double>(coef, batch, S, n0, scales, factor, flags, x_out, st);
+  return icwt_impl<float>(coef, batch, S, n0, scales, factor, flags, x_out, st);
 }

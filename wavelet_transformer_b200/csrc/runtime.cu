@@ -160,8 +160,17 @@ static void free_tables() {
 
 // ---- axes --------------------------------------------------------------------------
 int resolve_axes(int n0, double dt, double dj, double s0, int J, double f0, Axes *ax) {
+  Mother m;
+  m.param = f0;
+  return resolve_axes(n0, dt, dj, s0, J, m, ax);
+}
+
+int resolve_axes(int n0, double dt, double dj, double s0, int J, const Mother &m, Axes *ax) {
   WTB_REQUIRE(n0 > 0 && dt > 0 && dj > 0, WTB_EINVAL, "n0, dt and dj must be positive");
-  const double fl = morlet_flambda(f0);
+  WTB_REQUIRE(m.kind == WTB_MORLET || m.kind == WTB_PAUL || m.kind == WTB_DOG, WTB_EINVAL, "unknown mother wavelet %d", m.kind);
+  WTB_REQUIRE(m.kind == WTB_MORLET ? m.param > 0 : (m.param >= 1 && m.param <= 40 && m.param == std::floor(m.param)),
+              WTB_EINVAL, "mother wavelet parameter %g out of range", m.param);
+  const double fl = mother_flambda(m);
   if (s0 == -1) s0 = 2 * dt / fl;
   WTB_REQUIRE(s0 > 0, WTB_EINVAL, "s0 must be positive (or -1)");
   if (J == -1) J = (int)std::nearbyint(std::log2(n0 * dt / s0) / dj);
@@ -216,21 +225,29 @@ void wtb_shutdown(void) {
 
 const char *wtb_last_error(void) { return g_err; }
 
-int wtb_cwt_axes(int n0, double dt, double dj, double s0, int J, double f0, int *J_out,
-                 double *scales, double *freqs, double *coi) {
+int wtb_cwt_axes_mother(int n0, double dt, double dj, double s0, int J, int mother, double param, int *J_out,
+                        double *scales, double *freqs, double *coi) {
   Axes ax;
-  WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));
+  Mother m;
+  m.kind = mother;
+  m.param = param;
+  WTB_TRY(resolve_axes(n0, dt, dj, s0, J, m, &ax));
   if (J_out) *J_out = ax.J;
   for (int j = 0; j <= ax.J; ++j) {
     if (scales) scales[j] = ax.scales[j];
     if (freqs) freqs[j] = ax.freqs[j];
   }
   if (coi) {
-    // pycwt.cwt: flambda * coi() * dt * (n0/2 - |t - (n0-1)/2|), coi() = 1/sqrt(2)
-    const double c = morlet_flambda(f0) / std::sqrt(2.0) * dt;
+    // pycwt.cwt: flambda * coi() * dt * (n0/2 - |t - (n0-1)/2|), coi() = 1/sqrt(2) for Morlet
+    const double c = mother_flambda(m) * mother_coi(m) * dt;
     for (int t = 0; t < n0; ++t) coi[t] = c * (n0 / 2.0 - std::fabs(t - (n0 - 1) / 2.0));
   }
   return WTB_OK;
+}
+
+int wtb_cwt_axes(int n0, double dt, double dj, double s0, int J, double f0, int *J_out,
+                 double *scales, double *freqs, double *coi) {
+  return wtb_cwt_axes_mother(n0, dt, dj, s0, J, WTB_MORLET, f0, J_out, scales, freqs, coi);
 }
 
 int wtb_wct_mc_geometry(double dt, double dj, double s0, int J, double f0, int *nsurr, int *maxscale) {

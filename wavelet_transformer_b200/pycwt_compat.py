@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _shim
 
-__all__ = ["Morlet", "Paul", "DOG", "MexicanHat", "ar1", "ar1_spectrum", "significance", "cwt", "xwt",
+__all__ = ["Morlet", "Paul", "DOG", "MexicanHat", "ar1", "ar1_spectrum", "significance", "cwt", "icwt", "xwt",
            "wct", "wct_significance", "rednoise", "rect"]
 
 
@@ -57,21 +57,16 @@ class Morlet:
         return 1.0 / self.coi()
 
 
-class _StubMother:
-    """Paul / DOG are constructed at import time by the reference
-    (src/wct.py:36-41, constants/results_configs.py:53-58) but never selected
-    (XWT_MOTHER = "morlet"); the engine only transforms with Morlet."""
+class _NoSmooth:
+    """pycwt implements ``smooth`` (hence ``wct``) for Morlet only; Paul and DOG raise."""
 
-    name = "stub"
-
-    def _unsupported(self, *_a, **_k):
-        raise NotImplementedError(
-            f"{type(self).__name__}: only the Morlet wavelet is implemented on the B200 engine")
-
-    psi_ft = psi = smooth = _unsupported
+    def smooth(self, *_a, **_k):
+        raise NotImplementedError(f"{type(self).__name__}.smooth: pycwt only smooths with the Morlet wavelet")
 
 
-class Paul(_StubMother):
+class Paul(_NoSmooth):
+    """Paul wavelet of order m (pycwt.mothers.Paul; Torrence & Compo table 1)."""
+
     name = "paul"
 
     def __init__(self, m: int = 4):
@@ -82,14 +77,29 @@ class Paul(_StubMother):
         else:
             self.cdelta = self.gamma = self.deltaj0 = -1
 
+    def psi_ft(self, f):
+        f = np.asarray(f, dtype=float)
+        c = 2 ** self.m / np.sqrt(self.m * math.factorial(2 * self.m - 1))
+        return c * np.where(f > 0, f, 0.0) ** self.m * np.exp(-np.where(f > 0, f, 0.0)) * (f > 0)
+
+    def psi(self, t):
+        t = np.asarray(t, dtype=float)
+        c = 2 ** self.m * 1j ** self.m * math.factorial(self.m) / np.sqrt(np.pi * math.factorial(2 * self.m))
+        return c * (1 - 1j * t) ** (-(self.m + 1))
+
     def flambda(self):
         return 4 * np.pi / (2 * self.m + 1)
 
     def coi(self):
         return np.sqrt(2)
 
+    def sup(self):
+        return 1.0 / self.coi()
 
-class DOG(_StubMother):
+
+class DOG(_NoSmooth):
+    """Derivative-of-Gaussian wavelet of order m (m = 2: Mexican hat)."""
+
     name = "dog"
 
     def __init__(self, m: int = 2):
@@ -102,11 +112,24 @@ class DOG(_StubMother):
         else:
             self.cdelta = self.gamma = self.deltaj0 = -1
 
+    def psi_ft(self, f):
+        f = np.asarray(f, dtype=float)
+        return -(1j ** self.m) / np.sqrt(math.gamma(self.m + 0.5)) * f ** self.m * np.exp(-0.5 * f ** 2)
+
+    def psi(self, t):
+        from numpy.polynomial.hermite_e import hermeval
+        t = np.asarray(t, dtype=float)
+        he = hermeval(t, [0] * self.m + [1])
+        return (-1) ** (self.m + 1) * he * np.exp(-t ** 2 / 2) / np.sqrt(math.gamma(self.m + 0.5))
+
     def flambda(self):
         return 2 * np.pi / np.sqrt(self.m + 0.5)
 
     def coi(self):
         return 1.0 / np.sqrt(2)
+
+    def sup(self):
+        return 1.0 / self.coi()
 
 
 class MexicanHat(DOG):
@@ -116,14 +139,36 @@ class MexicanHat(DOG):
         super().__init__(m=2)
 
 
-def _as_morlet(wavelet) -> Morlet:
+_MOTHERS = {"morlet": Morlet, "paul": Paul, "dog": DOG, "mexicanhat": MexicanHat, "mexican hat": MexicanHat}
+
+
+def _as_mother(wavelet):
+    """pycwt._check_parameter_wavelet: a mother object or its name."""
     if isinstance(wavelet, str):
-        if wavelet.lower() == "morlet":
-            return Morlet(6)
-        raise NotImplementedError(f"wavelet '{wavelet}': only Morlet is implemented on the B200 engine")
+        try:
+            return _MOTHERS[wavelet.lower()]()
+        except KeyError:
+            raise ValueError(f"Unknown wavelet '{wavelet}'") from None
+    return wavelet
+
+
+def _mother_code(wavelet):
+    if isinstance(wavelet, Paul):
+        return _shim.PAUL, float(wavelet.m)
+    if isinstance(wavelet, DOG):
+        return _shim.DOG, float(wavelet.m)
+    if isinstance(wavelet, Morlet) or getattr(wavelet, "name", None) == "morlet":
+        return _shim.MORLET, float(wavelet.f0)
+    raise NotImplementedError(f"mother wavelet {wavelet!r} is not implemented on the B200 engine")
+
+
+def _as_morlet(wavelet) -> Morlet:
+    """XWT / WCT / significance run with Morlet only (pycwt smooths with Morlet only; the
+    reference never selects another mother, constants/results_configs.py:26)."""
+    wavelet = _as_mother(wavelet)
     if isinstance(wavelet, Morlet) or getattr(wavelet, "name", None) == "morlet":
         return wavelet
-    raise NotImplementedError("only the Morlet wavelet is implemented on the B200 engine")
+    raise NotImplementedError("cross-wavelet, coherence and significance use the Morlet wavelet only")
 
 
 def rect(n, normalize=False):
@@ -196,21 +241,21 @@ def significance(signal, dt, scales, sigma_test=0, alpha=None, significance_leve
 
 
 def _resolve_s0_J(n0, dt, dj, s0, J, wavelet):
-    Jr, scales, freqs, coi = _shim.cwt_axes(n0, dt, dj, s0, int(J) if J != -1 else -1, wavelet.f0)
-    return Jr, scales, freqs, coi
+    kind, param = _mother_code(wavelet)
+    return _shim.cwt_axes_mother(n0, dt, dj, s0, int(J) if J != -1 else -1, kind, param)
 
 
 def cwt(signal, dt, dj=1 / 12, s0=-1, J=-1, wavelet="morlet", freqs=None):
     """Continuous wavelet transform.  Returns ``(W, sj, freqs, coi, fft, fftfreqs)``
     with ``W`` complex128 of shape [J+1, n0]."""
-    wavelet = _as_morlet(wavelet)
+    wavelet = _as_mother(wavelet)
     if freqs is not None:
         raise NotImplementedError("custom `freqs` are not supported; use dj/s0/J")
     x = np.ascontiguousarray(signal, dtype=float)
     n0 = x.size
     Jr, sj, fr, coi = _resolve_s0_J(n0, dt, dj, s0, J, wavelet)
-    _, W = _shim.cwt_morlet(x, dt, dj, s0, Jr if J != -1 else -1, wavelet.f0,
-                            want_power=False, want_coef=True)
+    kind, param = _mother_code(wavelet)
+    _, W = _shim.cwt(x, dt, dj, s0, Jr if J != -1 else -1, kind, param, want_power=False, want_coef=True)
     W = np.asarray(W, dtype=np.complex128)
     # Side outputs pycwt also returns and the reference discards (src/cwt.py:109):
     # one O(N log N) host FFT, outside the hot path.
@@ -218,6 +263,22 @@ def cwt(signal, dt, dj=1 / 12, s0=-1, J=-1, wavelet="morlet", freqs=None):
     sft = np.fft.fft(x, N)
     ftfreqs = 2 * np.pi * np.fft.fftfreq(N, dt)
     return W, sj, fr, coi, sft[1:N // 2] / N ** 0.5, ftfreqs[1:N // 2] / (2 * np.pi)
+
+
+def icwt(W, sj, dt, dj=1 / 12, wavelet="morlet"):
+    """Inverse continuous wavelet transform (Torrence & Compo 1998, eq. 11):
+    ``dj sqrt(dt) / (C_delta psi_0(0)) * sum_j Re(W_j) / sqrt(s_j)``; the sum over scales runs
+    on the device.  ``W`` is [S, n0] (or its transpose, as pycwt accepts)."""
+    wavelet = _as_mother(wavelet)
+    W = np.asarray(W)
+    sj = np.asarray(sj, dtype=float)
+    a, b = W.shape
+    if a != sj.size:
+        if b != sj.size:
+            raise Warning("Input array dimensions do not match.")
+        W = W.T
+    factor = dj * np.sqrt(dt) / (wavelet.cdelta * np.real(wavelet.psi(0)))
+    return np.asarray(_shim.icwt(W, sj, factor, f64=True), dtype=float)
 
 
 def _normalised(y, normalize):
@@ -275,6 +336,23 @@ def _cache_file(al1, al2, dt, dj, s0, J, level, mc_count, seed, white, wavelet) 
     return root / f"{key}.gz"
 
 
+_PYCWT_NAMES = {"morlet": "Morlet", "paul": "Paul", "dog": "DOG", "mexicanhat": "Mexican Hat"}
+
+
+def pycwt_cache_file(al1, al2, dt, dj, s0, J, wavelet="morlet") -> Path:
+    """The file pycwt 0.4.0b0's ``wct_significance`` itself would use under ``~/.cache/pycwt``
+    (SURVEY A.7): ``wct_sig_{aa0:.5f}_{aa1:.5f}_{dj:.5f}_{s0/dt:.5f}_{J}_{name}.gz`` with
+    ``aa = round(arctanh([al1, al2] * 4))`` -- pycwt's own expression, which is NaN for any
+    coefficient above 0.25, so distinct AR(1) pairs share one file.  That collision is why this
+    cache is only consulted on request (``WTB_PYCWT_CACHE=read`` or ``readwrite``)."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        aa = np.round(np.arctanh(np.array([al1, al2], dtype=float) * 4.0))
+    aa = np.abs(aa) + 0.5 * (aa < 0)
+    name = _PYCWT_NAMES.get(getattr(_as_mother(wavelet), "name", "morlet"), "Morlet")
+    root = Path(os.environ.get("WTB_PYCWT_CACHE_DIR", Path.home() / ".cache" / "pycwt"))
+    return root / f"wct_sig_{aa[0]:0.5f}_{aa[1]:0.5f}_{dj:0.5f}_{s0 / dt:0.5f}_{int(J):d}_{name}.gz"
+
+
 def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="morlet", mc_count=300,
                      progress=True, cache=True, seed=0, white=False, surrogates=None, n_shards=1):
     """Monte Carlo coherence significance (one value per scale).
@@ -286,22 +364,26 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="
     wavelet = _as_morlet(wavelet)
     J = int(J)
     path = _cache_file(al1, al2, dt, dj, s0, J, significance_level, mc_count, seed, white, wavelet)
+    pycwt_mode = os.environ.get("WTB_PYCWT_CACHE", "").lower()
+    pycwt_path = pycwt_cache_file(al1, al2, dt, dj, s0, J, wavelet)
     if cache and surrogates is None:
-        try:
-            return np.loadtxt(path, unpack=True)
-        except OSError:
-            pass
+        for candidate in ([pycwt_path] if pycwt_mode in ("read", "readwrite") else []) + [path]:
+            try:
+                return np.loadtxt(candidate, unpack=True)
+            except OSError:
+                pass
     _, maxscale = _shim.wct_mc_geometry(dt, dj, s0, J, wavelet.f0)
     hist = _shim.wct_mc_hist(al1, al2, dt, dj, s0, J, wavelet.f0, mc_first=0, mc_count=mc_count,
                              seed=seed, surrogates=surrogates, white=white)
     has = _shim.row_has_points(dt, dj, s0, J, wavelet.f0)
     sig95 = _shim.wct_sig_from_hist(hist, maxscale, significance_level, has)
     if cache and surrogates is None:
-        try:
-            path.parent.mkdir(parents=True, exist_ok=True)
-            np.savetxt(path, sig95)
-        except OSError:
-            pass
+        for target in [path] + ([pycwt_path] if pycwt_mode == "readwrite" else []):
+            try:
+                target.parent.mkdir(parents=True, exist_ok=True)
+                np.savetxt(target, sig95)   # one float per line, gzip by suffix: pycwt's format
+            except OSError:
+                pass
     return sig95
 
 

@@ -4,10 +4,10 @@
 // One CTA of 256 threads owns one (pair, scale) row and carries the row's TWO fields
 // (two independent 4096-point FFTs) through every pass together: twiddles and index
 // arithmetic are shared, and the shared-memory exchanges move both fields with one
-// 128-bit access.  A 4096-point transform is three radix-16 passes; every thread keeps
+// 64-bit access per real / imaginary pair.  A 4096-point transform is three radix-16 passes; every thread keeps
 // its 2 x 16 points in registers (fft16_gen.cuh: Linzer-Feig FMA butterflies, literal
-// twiddles); passes exchange data through one padded float4 buffer (Stockham index
-// maps, in place).  Forward transforms run the same inverse code on conjugated data, so
+// twiddles); passes exchange data through two padded planes of float2 (real pairs, imaginary
+// pairs; Stockham index maps, in place).  Forward transforms run the same inverse code on conjugated data, so
 // one pass body (one copy of the code, instruction-cache resident) serves every round.
 //
 // The rounds of a row are chained through REGISTERS: pass 3 leaves thread j with
@@ -69,35 +69,51 @@ using fft32::mul2;
 // Inverse 4096-point transforms of both fields.  On entry R/I[br4(r)] hold input
 // j + 256 r (first 2^L of them non-zero); on exit R/I[r'] hold output j + 256 r'.
 // Contains 4 CTA barriers and ends with the buffer free.
-__device__ __forceinline__ void fft4096_inv2(float2 (&R)[16], float2 (&I)[16], int L, float4 *B,
+__device__ __forceinline__ void fft4096_inv2(float2 (&R)[16], float2 (&I)[16], int L, float2 *Bre, float2 *Bim,
                                              const float2 *__restrict__ tw2s,
                                              const float2 *__restrict__ tw3, int j) {
+  // The real and the imaginary pairs travel through two planes of 8-byte elements: a register
+  // pair goes out and comes back with one 64-bit access each, so no MOVs assemble 128-bit
+  // vectors, and every index below is `base + immediate` (pad(i) = i + (i >> 4) is spelled out
+  // per access pattern because the compiler cannot see that the shifts never carry).
   const int k2 = j & 15;
   fft16::dit16p_inv(R, I, L);
-  // exchange 1: pass-1 output index 16 j + r'
+  // exchange 1: pass-1 output index 16 j + r'  ->  pad = 17 j + r'
+  {
+    float2 *wre = Bre + 17 * j, *wim = Bim + 17 * j;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) B[pad(16 * j + r)] = make_float4(R[r].x, R[r].y, I[r].x, I[r].y);
+    for (int r = 0; r < 16; ++r) {
+      wre[r] = R[r];
+      wim[r] = I[r];
+    }
+  }
   __syncthreads();
+  // reads of index j + 256 r  ->  pad = j + (j >> 4) + 272 r
+  const float2 *rre = Bre + j + (j >> 4), *rim = Bim + j + (j >> 4);
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const float4 q = B[pad(j + 256 * r)];
+    const float2 qr = rre[272 * r], qi = rim[272 * r];
     const float2 w = tw2s[r * 16 + k2];
-    const float2 qr = make_float2(q.x, q.y), qi = make_float2(q.z, q.w);
     R[br4(r)] = fma2(qi, bc(-w.y), mul2(qr, bc(w.x)));
     I[br4(r)] = fma2(qr, bc(w.y), mul2(qi, bc(w.x)));
   }
   __syncthreads();
   fft16::dit16p_inv(R, I, 4);
-  // exchange 2: pass-2 output index (j - k2) * 16 + k2 + 16 r'
-  const int j0 = ((j - k2) << 4) + k2;
+  // exchange 2: pass-2 output index (j - k2) * 16 + k2 + 16 r'  ->  pad = 17 (j - k2) + k2 + 17 r'
+  {
+    const int base = 17 * (j - k2) + k2;
+    float2 *wre = Bre + base, *wim = Bim + base;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) B[pad(j0 + 16 * r)] = make_float4(R[r].x, R[r].y, I[r].x, I[r].y);
+    for (int r = 0; r < 16; ++r) {
+      wre[17 * r] = R[r];
+      wim[17 * r] = I[r];
+    }
+  }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const float4 q = B[pad(j + 256 * r)];
+    const float2 qr = rre[272 * r], qi = rim[272 * r];
     const float2 w = __ldg(&tw3[r * 256 + j]);
-    const float2 qr = make_float2(q.x, q.y), qi = make_float2(q.z, q.w);
     R[br4(r)] = fma2(qi, bc(-w.y), mul2(qr, bc(w.x)));
     I[br4(r)] = fma2(qr, bc(w.y), mul2(qi, bc(w.x)));
   }
@@ -113,8 +129,9 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
                 float4 *__restrict__ spec, float *__restrict__ phase, float2 *__restrict__ w12,
                 int smooth) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *B = reinterpret_cast<float4 *>(smem_raw);                  // [kBuf]
-  float2 *tw2s = reinterpret_cast<float2 *>(B + kBuf);               // [256]
+  float2 *Bre = reinterpret_cast<float2 *>(smem_raw);                // [kBuf] real pairs
+  float2 *Bim = Bre + kBuf;                                          // [kBuf] imaginary pairs
+  float2 *tw2s = Bim + kBuf;                                         // [256]
   const int j = threadIdx.x;
   tw2s[j] = tw2[j];
   const int64_t row = blockIdx.x;
@@ -144,7 +161,7 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
   int L = rp.L1;
 #pragma unroll 1
   for (int round = 0; round < 2; ++round) {
-    fft4096_inv2(R, I, L, B, tw2s, tw3, j);
+    fft4096_inv2(R, I, L, Bre, Bim, tw2s, tw3, j);
     if (round == 1) break;
     // pointwise step: lane 0 becomes P = (|W1|^2 + i |W2|^2)/s, lane 1 becomes
     // C = W1 conj(W2)/s.  Both are CONJUGATED so that round 2 (a forward transform) can
@@ -256,8 +273,9 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
                float *__restrict__ wct, unsigned long long *__restrict__ hist,
                const int *__restrict__ tlo, const int *__restrict__ thi, int maxscale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *B = reinterpret_cast<float4 *>(smem_raw);
-  float2 *tw2s = reinterpret_cast<float2 *>(B + kBuf);
+  float2 *Bre = reinterpret_cast<float2 *>(smem_raw);
+  float2 *Bim = Bre + kBuf;
+  float2 *tw2s = Bim + kBuf;
   unsigned int *shist = reinterpret_cast<unsigned int *>(tw2s + 256);   // MODE 1: 1000 bins
   const int j = threadIdx.x;
   const int64_t row = blockIdx.x;
@@ -281,7 +299,7 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
     I[br4(r)] = make_float2(g.z, g.w);
   }
   __syncthreads();   // tw2s / shist visible
-  fft4096_inv2(R, I, 4, B, tw2s, tw3, j);
+  fft4096_inv2(R, I, 4, Bre, Bim, tw2s, tw3, j);
   // lane 0 = S1 + i S2 (two real fields), lane 1 = S12
   if (MODE == 0) {
     float *orow = wct + row * (int64_t)n0;

@@ -19,6 +19,8 @@
 // the daughter peak, far inside the FP32 tolerance): negative frequencies, and
 // bins above k_hi(s) = (f0 + 5.3) N dt / (2 pi s).  Rows with k_hi < 32 need no
 // step A and no transpose; rows with fewer non-zero inputs skip butterfly stages.
+#include <type_traits>
+
 #include "common.cuh"
 #include "fft32_gen.cuh"
 
@@ -33,7 +35,7 @@ using fft32::fma2;
 using fft32::mul2;
 
 constexpr int kN = 1024;
-constexpr int kWarps = 16;            // warps per CTA, one CTA per SM
+constexpr int kWarpsDefault = 16;     // warps per CTA, one CTA per SM (WTB_CWT_WARPS overrides: 12, 14, 15)
 constexpr int kTrStride = 34;         // floats per row of the transpose buffer (even, == 2 mod 32)
 constexpr float kZCut = 5.3f;         // daughter dropped where |s*w - f0| > kZCut  (exp(-14) ~ 8e-7)
 constexpr int kMaxRows = 256;         // scale rows staged in shared memory
@@ -54,7 +56,7 @@ struct WarpSmem {
   float yi[32];
 };
 
-struct CtaSmem {
+template <int kWarps> struct CtaSmem {
   // exp(+2*pi*i*a*b/1024) tables, float4 = (re_0, re_1, im_0, im_1) for a packed pair
   float4 tw_a[16][32];              // pair (t2, t2+16) x k1=lane   : step A output twiddle
   float4 tw_b[16][32];              // pair (2m, 2m+1)  x t2=lane   : single-pass input twiddle
@@ -79,11 +81,12 @@ __device__ __forceinline__ constexpr int below_pow2(int m) {
 
 // One dit32 call site serves the forward transform (s = -1), step A and step B of
 // every scale row: the hot code stays inside the instruction cache.
+template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
                 const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CtaSmem &sm = *reinterpret_cast<CtaSmem *>(smem_raw);
+  CtaSmem<kWarps> &sm = *reinterpret_cast<CtaSmem<kWarps> *>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
@@ -253,13 +256,24 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
   RowParam *d_rows = (RowParam *)scratch;
   // rows.data() is pageable: the copy is staged before the call returns
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
-  const size_t smem = sizeof(CtaSmem);
-  WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t ctas_needed = (batch + kWarps - 1) / kWarps;
-  const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count());
-  k_cwt_fast_1024<<<grid, kWarps * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
-  WTB_LAUNCH_CHECK();
-  return WTB_OK;
+  int warps = kWarpsDefault;
+  if (const char *e = std::getenv("WTB_CWT_WARPS")) warps = std::atoi(e);
+  auto launch = [&](auto tag) -> int {
+    constexpr int W = decltype(tag)::value;
+    const size_t smem = sizeof(CtaSmem<W>);
+    WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ctas_needed = (batch + W - 1) / W;
+    const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count());
+    k_cwt_fast_1024<W><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
+    WTB_LAUNCH_CHECK();
+    return WTB_OK;
+  };
+  switch (warps) {
+    case 12: return launch(std::integral_constant<int, 12>{});
+    case 14: return launch(std::integral_constant<int, 14>{});
+    case 15: return launch(std::integral_constant<int, 15>{});
+    default: return launch(std::integral_constant<int, 16>{});
+  }
 }
 
 }  // namespace wtb

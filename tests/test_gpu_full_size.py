@@ -66,3 +66,47 @@ def test_cfg5_histogram_totals_and_partition(shim):
     assert np.isfinite(sig[:maxscale]).all() and ((sig[:maxscale] > 0.55) & (sig[:maxscale] < 0.999)).all()
     # thresholds are a smooth function of scale away from the largest scales
     assert np.abs(np.diff(sig[5:50])).max() < 0.05
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n", [1024, 1333])
+def test_cfg2_batched_modwt_properties(shim, n):
+    """cfg2 shape at batch scale: 100 000 series x N (the reference's 1333-sample series and a
+    power of two), LA8, J = 6, FP64, device resident.  Energy conservation, perfect
+    reconstruction, MRA additivity, DWT round trip, and oracle parity on sampled rows."""
+    import torch
+    from oracle import modwt_oracle as mo
+    from oracle import pywt_oracle as pw
+    dev = torch.device("cuda", 0)
+    B, J = 100_000, 6
+    w8 = pw.Wavelet("sym4")
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    x = torch.randn((B, n), generator=g, device=dev, dtype=torch.float64)
+    w = torch.empty((B, J + 1, n), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    shim.modwt_device(x.data_ptr(), B, n, w8.dec_lo, w8.dec_hi, J, w.data_ptr(), f64=True, stream=st)
+    torch.cuda.synchronize()
+    energy = (w ** 2).sum(dim=(1, 2))
+    assert float(((energy - (x ** 2).sum(dim=1)).abs() / energy).max()) < 1e-10   # the tabulated taps are orthonormal to ~1e-12
+    rec = torch.empty_like(x)
+    shim.imodwt_device(w.data_ptr(), B, n, w8.dec_lo, w8.dec_hi, J, rec.data_ptr(), f64=True, stream=st)
+    assert float((rec - x).abs().max()) < 1e-10
+    mra = torch.empty_like(w)
+    shim.modwtmra_taps_device(w.data_ptr(), B, n, w8.dec_lo, w8.dec_hi, J, mra.data_ptr(), f64=True, stream=st)
+    assert float((mra.sum(dim=1) - x).abs().max()) < 1e-10
+    for b in (0, 31_337, B - 1):
+        xb = x[b].cpu().numpy()
+        ref = mo.modwt(xb, "sym4", J)
+        assert np.abs(w[b].cpu().numpy() - ref).max() < 1e-12
+        assert np.abs(mra[b].cpu().numpy() - mo.modwtmra(ref, "sym4")).max() < 1e-11
+    level = pw.dwt_max_level(n, 8)
+    lens = shim.dwt_coeff_lens(n, 8, level)
+    pk = torch.empty((B, int(lens.sum())), dtype=torch.float64, device=dev)
+    shim.wavedec_device(x.data_ptr(), B, n, w8.dec_lo, w8.dec_hi, level, pk.data_ptr(), f64=True, stream=st)
+    xr = torch.empty((B, shim.waverec_len(lens, 8)), dtype=torch.float64, device=dev)
+    shim.waverec_device(pk.data_ptr(), B, lens, w8.rec_lo, w8.rec_hi, xr.data_ptr(), f64=True, stream=st)
+    off = xr.shape[1] - n                     # odd lengths reconstruct one sample long (dwt.py:82-85)
+    assert float((xr[:, : n] - x).abs().max()) < 1e-9 if off == 0 else xr.shape[1] == n + 1
+    b = 77_777
+    assert np.abs(pk[b].cpu().numpy() - np.concatenate(pw.wavedec(x[b].cpu().numpy(), "sym4", level=level))).max() < 1e-12

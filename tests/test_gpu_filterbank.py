@@ -240,3 +240,25 @@ def test_blocked_kernels_any_row_alignment(shim, f64, n):
         xr = buf(ref_rec.shape, off_in)
         shim.waverec_device(pk.data_ptr(), B, lens, rlo, rhi, xr.data_ptr(), f64=f64, stream=st)
         assert np.abs(xr.cpu().numpy() - ref_rec).max() <= tol
+
+
+def test_modwt_single_step_helpers(shim, series):
+    """circular_convolve_d / _s / _mra (modwt.py:81-123): one analysis, synthesis and MRA step
+    with the reference's argument conventions, against the oracle's gather formulas."""
+    from src import modwt
+    x = series["expectation_value"]
+    N = x.size
+    g, h = np.array(pw.Wavelet("sym4").dec_lo) / np.sqrt(2), np.array(pw.Wavelet("sym4").dec_hi) / np.sqrt(2)
+    for j in (1, 3, 6, 8):                                       # 2^7 * 7 > 565: the kernel folds more than once
+        w_ref, v_ref = mo._circ_gather(x, h, 2 ** (j - 1), -1), mo._circ_gather(x, g, 2 ** (j - 1), -1)
+        w = modwt.circular_convolve_d(h, x, j)
+        v = modwt.circular_convolve_d(g, x, j)
+        assert np.abs(w - w_ref).max() <= 1e-12 and np.abs(v - v_ref).max() <= 1e-12
+        back = modwt.circular_convolve_s(h, g, w, v, j)
+        ref_back = mo._circ_gather(w_ref, h, 2 ** (j - 1), 1) + mo._circ_gather(v_ref, g, 2 ** (j - 1), 1)
+        assert np.abs(back - ref_back).max() <= 1e-12
+        assert np.abs(back - x).max() <= 1e-10                   # one level inverts exactly
+    filt = mo.mra_filters("sym4", 4, N)
+    wfull = mo.modwt(x, "sym4", 4)
+    for r in (0, 3, 4):
+        assert np.abs(modwt.circular_convolve_mra(filt[r], wfull[r]) - mo.modwtmra(wfull, "sym4")[r]).max() <= 1e-12

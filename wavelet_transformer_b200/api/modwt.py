@@ -39,6 +39,47 @@ def period_list(li, N):
     return f if f.size < 2 * N else f.reshape(-1, N).sum(axis=0)
 
 
+def _correlate_rows(rows, filters_periodised):
+    """out[r, t] = sum_m f[r, m] rows[r, (t + m) mod N] on the device (wtb_modwtmra); the kernel
+    wants at least two rows, so a single row is sent twice."""
+    rows = np.atleast_2d(np.asarray(rows, dtype=float))
+    filt = np.atleast_2d(np.asarray(filters_periodised, dtype=float))
+    if rows.shape[0] == 1:
+        return np.asarray(_shim.modwtmra(np.vstack([rows, rows]), np.vstack([filt, filt])), dtype=float)[:1]
+    return np.asarray(_shim.modwtmra(rows, filt), dtype=float)
+
+
+def _dilated_periodised(taps, j, N, sign):
+    """f[(sign * 2^(j-1) * l) mod N] += taps[l]: the level-j a-trous filter folded onto N samples."""
+    f = np.zeros(N)
+    np.add.at(f, (sign * 2 ** (j - 1) * np.arange(len(taps))) % N, np.asarray(taps, dtype=float))
+    return f
+
+
+def circular_convolve_mra(h_j_o, w_j):
+    """One MRA row: sum_l h_j_o[l] w_j[(t + l) mod N] (modwt.py:81-83)."""
+    w_j = np.asarray(w_j, dtype=float)
+    f = np.zeros(w_j.size)
+    f[: len(h_j_o)] = h_j_o
+    return _correlate_rows(w_j, f)[0]
+
+
+def circular_convolve_d(h_t, v_j_1, j):
+    """Level-j analysis step w_j[t] = sum_l h_t[l] v_{j-1}[(t - 2^(j-1) l) mod N] (modwt.py:86-102)."""
+    v = np.asarray(v_j_1, dtype=float)
+    return _correlate_rows(v, _dilated_periodised(h_t, j, v.size, -1))[0]
+
+
+def circular_convolve_s(h_t, g_t, w_j, v_j, j):
+    """Level-j synthesis step v_{j-1}[t] = sum_l h_t[l] w_j[(t + 2^(j-1) l) mod N]
+    + g_t[l] v_j[(t + 2^(j-1) l) mod N] (modwt.py:105-123)."""
+    w = np.asarray(w_j, dtype=float)
+    both = _correlate_rows(np.vstack([w, np.asarray(v_j, dtype=float)]),
+                           np.vstack([_dilated_periodised(h_t, j, w.size, 1),
+                                      _dilated_periodised(g_t, j, w.size, 1)]))
+    return both[0] + both[1]
+
+
 def modwt(x, filters, level):
     """Rows w_1..w_J, v_J of the maximal-overlap DWT (modwt.py:126-144)."""
     g, h = _bank(filters)

@@ -33,7 +33,7 @@ using fft16::br4;
 
 constexpr int kN = 4096;
 constexpr int kThreads = 256;
-constexpr int kBuf = kN + kN / 16;     // padded: index i lives at i + (i >> 4)
+constexpr int kBuf = kN + kN / 16;     // padded: index i lives at pad(i) = i + (i >> 4)
 constexpr int kMaxRowsC = 512;         // scale rows the boxcar kernel stages in shared memory
 
 struct WRow {
@@ -57,7 +57,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 
 using fft32::bc;
 using fft32::fma2;

@@ -172,3 +172,49 @@ def test_significance_cache_files(tmp_path, monkeypatch):
     np.savetxt(target, sig)
     got = wavelet.wct_significance(0.1, 0.2, dt=1 / 12, dj=1 / 8, s0=1 / 6, J=65)   # served from the file: no GPU call
     assert np.allclose(got, sig)
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    from wavelet_transformer_b200 import _build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    lib_dir = _build.LIB.parent
+    exe = tmp_path / "c_abi_demo"
+    subprocess.run([gcc, "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "c_abi_demo.c"),
+                    "-o", str(exe), f"-L{lib_dir}", "-lwavelet_sm100a", f"-Wl,-rpath,{lib_dir}", "-lm"], check=True)
+    return exe
+
+
+def test_c_abi_links_from_plain_c(tmp_path):
+    """include/wtb.h is valid C and every entry point the demo uses links from gcc; without a
+    GPU the program fails loudly through the status code / wtb_last_error path."""
+    import subprocess
+    import torch
+    exe = _build_c_demo(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run is covered by the gpu-marked test")
+    proc = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert proc.returncode == 1 and "no CPU fallback" in proc.stderr
+
+
+@pytest.mark.gpu
+def test_c_abi_demo_matches_python(tmp_path):
+    import subprocess
+    from oracle import modwt_oracle as mo
+    from oracle import pycwt_oracle as po
+    exe = _build_c_demo(tmp_path)
+    proc = subprocess.run([str(exe)], capture_output=True, text=True, check=True)
+    fields = dict(kv.split("=") for kv in proc.stdout.split())
+    t = np.arange(600)
+    x = np.sin(2 * np.pi * t / 37.0) + 0.5 * np.cos(2 * np.pi * t / 90.0)
+    W, sj, *_ = po.cwt(x, 1 / 12, 1 / 12, 2 / 12, -1)
+    power = np.abs(W) ** 2
+    assert int(fields["S"]) == sj.size
+    assert float(fields["power_sum"]) == pytest.approx(power.sum(), rel=1e-9)
+    assert float(fields["peak_scale"]) == pytest.approx(sj[np.unravel_index(power.argmax(), power.shape)[0]], rel=1e-6)
+    w = mo.modwt(x, "sym4", 4)
+    assert float(fields["modwt_energy_ratio"]) == pytest.approx((w ** 2).sum() / (x ** 2).sum(), abs=1e-10)
+    assert float(fields["imodwt_err"]) < 1e-10 and int(fields["launches"]) >= 4

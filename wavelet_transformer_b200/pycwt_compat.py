@@ -329,10 +329,10 @@ def wct(y1, y2, dt, dj=1 / 12, s0=-1, J=-1, sig=True, significance_level=0.95, w
     return np.asarray(WCT, dtype=float), np.asarray(aWCT, dtype=float), coi, freq, sig
 
 
-def _cache_file(al1, al2, dt, dj, s0, J, level, mc_count, seed, white, wavelet) -> Path:
+def _cache_file(al1, al2, dt, dj, s0, J, level, mc_count, seed, white, wavelet, prec=None) -> Path:
     root = Path(os.environ.get("WTB_CACHE_DIR", Path.home() / ".cache" / "wavelet_b200"))
     key = (f"wct_sig_{al1:.10f}_{al2:.10f}_{dj:.6f}_{s0 / dt:.6f}_{J:d}_{level:.4f}_{mc_count:d}_{seed:d}_"
-           f"{'white' if white else 'ar1'}_{wavelet.name}_{_shim.get_precision()}")
+           f"{'white' if white else 'ar1'}_{wavelet.name}_{prec or _shim.get_precision()}")
     return root / f"{key}.gz"
 
 
@@ -354,16 +354,26 @@ def pycwt_cache_file(al1, al2, dt, dj, s0, J, wavelet="morlet") -> Path:
 
 
 def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="morlet", mc_count=300,
-                     progress=True, cache=True, seed=0, white=False, surrogates=None, n_shards=1):
+                     progress=True, cache=True, seed=0, white=False, surrogates=None, n_shards=1,
+                     precision=None):
     """Monte Carlo coherence significance (one value per scale).
 
     Runs entirely on the GPU: Philox AR(1) surrogates -> CWT -> smoothing ->
     coherence -> per-scale histograms.  ``cache=True`` stores the result on disk
     keyed on the exact arguments (pycwt keeps a similar cache under
-    ~/.cache/pycwt).  ``surrogates`` ([mc_count, 2, N]) injects ready-made noise."""
+    ~/.cache/pycwt).  ``surrogates`` ([mc_count, 2, N]) injects ready-made noise.
+
+    ``precision``: "fp32" | "fp64" | None.  None keeps the global precision when surrogates
+    are injected (the per-realisation parity mode) and uses the FP32 register-FFT kernels with
+    the device RNG: the thresholds are Monte Carlo estimates with errors of order 1e-2, seven
+    orders above FP32 round-off (WTB_MC_PRECISION=fp64 restores the global setting)."""
     wavelet = _as_morlet(wavelet)
     J = int(J)
-    path = _cache_file(al1, al2, dt, dj, s0, J, significance_level, mc_count, seed, white, wavelet)
+    if precision is None and surrogates is None and os.environ.get("WTB_MC_PRECISION", "fp32").lower() != "fp64":
+        precision = "fp32"
+    f64 = None if precision is None else {"fp32": False, "fp64": True}[precision.lower()]
+    path = _cache_file(al1, al2, dt, dj, s0, J, significance_level, mc_count, seed, white, wavelet,
+                       None if precision is None else precision.lower())
     pycwt_mode = os.environ.get("WTB_PYCWT_CACHE", "").lower()
     pycwt_path = pycwt_cache_file(al1, al2, dt, dj, s0, J, wavelet)
     if cache and surrogates is None:
@@ -374,7 +384,7 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="
                 pass
     _, maxscale = _shim.wct_mc_geometry(dt, dj, s0, J, wavelet.f0)
     hist = _shim.wct_mc_hist(al1, al2, dt, dj, s0, J, wavelet.f0, mc_first=0, mc_count=mc_count,
-                             seed=seed, surrogates=surrogates, white=white)
+                             seed=seed, surrogates=surrogates, white=white, f64=f64)
     has = _shim.row_has_points(dt, dj, s0, J, wavelet.f0)
     sig95 = _shim.wct_sig_from_hist(hist, maxscale, significance_level, has)
     if cache and surrogates is None:

@@ -320,8 +320,20 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
   const bool dev = flags & WTB_DEVICE_PTRS;
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t per_pair = sizeof(T) * 2 * (size_t)nsurr + pair_bytes<T>(nsurr, N, S);
-  const size_t budget = size_t(3) << 29;  // 1.5 GiB of intermediates per chunk
-  const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(mc_count, (int64_t)(budget / per_pair)));
+  // Intermediates per chunk.  Launch tails are what chunking costs (1.5 GiB chunks: 253 k pairs/s,
+  // one 18 GB chunk: 263 k at 2048 pairs), so the default spends a tenth of the 180 GB HBM3e;
+  // chunks are balanced so that no short tail chunk is left over.
+  size_t budget = size_t(20) << 30;
+  if (const char *e = std::getenv("WTB_MC_CHUNK_MB")) {
+    budget = (size_t)std::max(1, std::atoi(e)) << 20;
+  } else {
+    size_t free_b = 0, total_b = 0;  // never ask for more than half of what is free right now
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+      budget = std::max(size_t(3) << 29, std::min(budget, free_b / 2));
+  }
+  const int64_t rows_max = std::max<int64_t>(1, (int64_t)(budget / per_pair));
+  const int64_t n_chunks = (mc_count + rows_max - 1) / rows_max;
+  const int64_t rows = std::max<int64_t>(1, (mc_count + n_chunks - 1) / std::max<int64_t>(1, n_chunks));
   void *stage = nullptr;
   const size_t b_hist = al(sizeof(uint64_t) * S * WTB_NBINS);
   WTB_TRY(staging_reserve(al(sizeof(T) * rows * 2 * nsurr) + b_hist, &stage));

@@ -263,6 +263,68 @@ k_wct_boxcar_4096(float4 *__restrict__ spec, int S, const WRow *__restrict__ row
   }
 }
 
+// The same boxcar for a compile-time tap count: K input rows per trip of the outer loop, so the
+// ring slot of every row is a compile-time index and the ring lives in REGISTERS (K float4):
+// no shared-memory traffic at all, taps in registers too.  Same sums in the same order as the
+// generic kernel above (bit-identical output).
+template <int K, int H>
+__global__ void __launch_bounds__(kThreads)
+k_wct_boxcar_4096_t(float4 *__restrict__ spec, int S, const WRow *__restrict__ rows, CohWin win) {
+  static_assert(K % H == 0, "loads are issued in K / H batches");
+  __shared__ int s_kc[kMaxRowsC];
+  const int tid = threadIdx.x;
+  for (int q = tid; q < S; q += kThreads) s_kc[q] = rows[q].kc;
+  __syncthreads();
+  const int64_t pair = blockIdx.x >> 4;
+  const int bin = ((blockIdx.x & 15) << 8) + tid;
+  const int akk = bin < kN / 2 ? bin : kN - bin;
+  if (akk > s_kc[0]) return;
+  int s_max = 0;
+  while (s_max + 1 < S && akk <= s_kc[s_max + 1]) ++s_max;
+  float4 *col = spec + pair * (int64_t)S * kN + bin;
+  constexpr int up = (K - 1) / 2;
+  const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float wk[K];
+  float4 ring[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    wk[k] = win.w[k];
+    ring[k] = zero;
+  }
+  const int s_end = min(S + up, s_max + K);
+  for (int base = 0; base < s_end; base += K) {
+#pragma unroll
+    for (int half = 0; half < K; half += H) {
+      float4 v[H];
+#pragma unroll
+      for (int q = 0; q < H; ++q)                            // H independent loads in flight
+        v[q] = (base + half + q <= s_max) ? col[(int64_t)(base + half + q) * kN] : zero;
+#pragma unroll
+      for (int q = 0; q < H; ++q) {
+        const int slot = half + q;                           // compile-time after unrolling
+        const int s_in = base + slot;
+        if (s_in < s_end) {
+          ring[slot] = v[q];
+          const int i = s_in - up;                           // output row completed by this input
+          if (i >= 0 && i < S) {
+            const int first = i + up - (K - 1);
+            if (akk <= s_kc[first < 0 ? 0 : first]) {
+              float4 acc = zero;
+#pragma unroll
+              for (int k = 0; k < K; ++k) {                  // k = 0 <-> row s_in, then older rows
+                const float4 g = ring[(slot - k + K) % K];
+                acc.x = fmaf(wk[k], g.x, acc.x); acc.y = fmaf(wk[k], g.y, acc.y);
+                acc.z = fmaf(wk[k], g.z, acc.z); acc.w = fmaf(wk[k], g.w, acc.w);
+              }
+              col[(int64_t)i * kN] = acc;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Kernel B: one CTA = one (pair, scale i): boxcar over the neighbouring rows' filtered
 // spectra, inverse transform, coherence -> plane (MODE 0) or per-scale histogram (MODE 1).
 template <int MODE>
@@ -417,10 +479,17 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
   cw.up = win.up;
   for (int k = 0; k < win.K; ++k) cw.w[k] = (float)win.w[k];
   {
-    const size_t smem_c = sizeof(float4) * (size_t)cw.K * kThreads;
-    WTB_CUDA(cudaFuncSetAttribute(k_wct_boxcar_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    k_wct_boxcar_4096<<<(unsigned)(pairs * 16), kThreads, smem_c, st>>>(spec, S, d_rows, cw);
-    WTB_LAUNCH_CHECK();
+    auto run = [&](auto kern, size_t smem_c) -> int {
+      WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+      kern<<<(unsigned)(pairs * 16), kThreads, smem_c, st>>>(spec, S, d_rows, cw);
+      WTB_LAUNCH_CHECK();
+      return WTB_OK;
+    };
+    // rect(round(0.6 / dj * 2)) taps: 10 at dj = 1/8, 14 at dj = 1/12, 5 at dj = 1/4
+    if (cw.K == 10 && cw.up == 4) WTB_TRY(run(k_wct_boxcar_4096_t<10, 5>, 0));
+    else if (cw.K == 14 && cw.up == 6) WTB_TRY(run(k_wct_boxcar_4096_t<14, 7>, 0));
+    else if (cw.K == 5 && cw.up == 2) WTB_TRY(run(k_wct_boxcar_4096_t<5, 5>, 0));
+    else WTB_TRY(run(k_wct_boxcar_4096, sizeof(float4) * (size_t)cw.K * kThreads));
   }
   if (d_hist) {
     WTB_CUDA(cudaFuncSetAttribute(k_wct_coh_4096<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));

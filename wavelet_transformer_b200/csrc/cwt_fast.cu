@@ -170,10 +170,8 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           __syncwarp();
         }
       }
-#pragma unroll 1
-      for (;;) {
-        fft32::dit32(R, I, L);
-        if (!two_pass) break;
+      fft32::dit32(R, I, L);        // the pruned site: step A, or the only pass of a narrow row
+      if (two_pass) {
         // step A done (lane = k1): twiddle by w1024^(k1 t2), transpose, reload with lane = t2
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
@@ -191,8 +189,7 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           I[br4(m)] = make_float2(ws.tri[(2 * m) * kTrStride + tidx], ws.tri[(2 * m + 1) * kTrStride + tidx]);
         }
         __syncwarp();
-        L = 5;
-        two_pass = 0;
+        fft32::dit32(R, I, 5);      // step B is always a full transform: its own straight-line site
       }
       if (s < 0) {
         // X^[lane + 32 t1] = conj(u[t1]), t1 < 16 (positive frequencies only)

@@ -157,11 +157,10 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
     }
   }
   __syncthreads();   // tw2s visible
-  int L = rp.L1;
-#pragma unroll 1
-  for (int round = 0; round < 2; ++round) {
-    fft4096_inv2(R, I, L, Bre, Bim, tw2s, tw3, j);
-    if (round == 1) break;
+  // round 1: W1, W2 (pruned first pass); its own call site, so round 2 below is straight-line
+  // code with a compile-time full first pass and no loop-carried copies of the 64 data registers
+  fft4096_inv2(R, I, rp.L1, Bre, Bim, tw2s, tw3, j);
+  {
     // pointwise step: lane 0 becomes P = (|W1|^2 + i |W2|^2)/s, lane 1 becomes
     // C = W1 conj(W2)/s.  Both are CONJUGATED so that round 2 (a forward transform) can
     // reuse the inverse code: FFT(x) = conj(IFFT(conj(x))).
@@ -186,8 +185,8 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
     if (!smooth) return;
 #pragma unroll
     for (int r = 0; r < 16; ++r) { R[r] = nR[r]; I[r] = nI[r]; }
-    L = 4;
   }
+  fft4096_inv2(R, I, 4, Bre, Bim, tw2s, tw3, j);   // round 2
   // (R, I) = conj(FFT(field)); Gaussian filter in the Fourier domain with the 1/N of the
   // inverse.  Bins where the filter is negligible are neither stored nor ever read.
   float4 *srow = spec + row * (int64_t)kN;

@@ -1,0 +1,107 @@
+"""GPU: degenerate and boundary inputs through every C entry point -- empty batches, the
+shortest series each transform accepts, single scales, one-element coefficient blocks,
+ragged batches split by length -- checked against the oracle where there is an answer and
+for a clean error where there is none."""
+
+import numpy as np
+import pytest
+
+from oracle import modwt_oracle as mo
+from oracle import pycwt_oracle as po
+from oracle import pywt_oracle as pw
+
+pytestmark = pytest.mark.gpu
+
+DT = 1 / 12
+
+
+def test_empty_batches_are_noops(shim):
+    lo, hi = np.array(pw.Wavelet("db4").dec_lo), np.array(pw.Wavelet("db4").dec_hi)
+    assert shim.cwt_morlet(np.zeros((0, 64)), DT, 1 / 4, 2 * DT, 8, f64=True)[0].shape == (0, 9, 64)
+    assert shim.modwt(np.zeros((0, 64)), lo, hi, 3, f64=True).shape == (0, 4, 64)
+    assert shim.imodwt(np.zeros((0, 4, 64)), lo, hi, f64=True).shape == (0, 64)
+    assert shim.modwtmra_taps(np.zeros((0, 4, 64)), lo, hi, f64=True).shape == (0, 4, 64)
+    packed, lens = shim.wavedec(np.zeros((0, 64)), lo, hi, 2, f64=True)
+    assert packed.shape == (0, int(lens.sum()))
+    assert shim.waverec(packed, lens, lo[::-1].copy(), hi[::-1].copy(), f64=True).shape[0] == 0
+    assert shim.series_prep(np.zeros((0, 16)), f64=True)[0].shape == (0, 16)
+    assert shim.xwt_wct(np.zeros((0, 64)), np.zeros((0, 64)), DT, 1 / 4, 2 * DT, 8, f64=True)[0].shape == (0, 9, 64)
+    h = shim.wct_mc_hist(0.5, 0.5, DT, 1 / 4, 2 * DT, 8, mc_count=0, f64=False)
+    assert h.sum() == 0
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_cwt_shortest_series_and_single_scale(shim, f64):
+    rng = np.random.default_rng(1)
+    for n0, J in ((3, 2), (4, 0), (5, 0), (33, 11)):     # n0 = 2 is NaN in pycwt itself (sqrt of a negative frequency)
+        x = rng.standard_normal(n0)
+        ref = np.abs(po.cwt(x, DT, 1 / 4, 2 * DT, J)[0]) ** 2
+        power, _ = shim.cwt_morlet(x, DT, 1 / 4, 2 * DT, J, f64=f64)
+        assert power.shape == (J + 1, n0)
+        assert np.abs(power - ref).max() <= (1e-10 if f64 else 1e-4) * max(ref.max(), 1e-30)
+    y1, y2 = rng.standard_normal(9), rng.standard_normal(9)
+    wct, ph, _ = shim.xwt_wct(y1, y2, DT, 1 / 2, 2 * DT, 3, f64=True)
+    ref = po.wct(y1, y2, DT, dj=1 / 2, s0=2 * DT, J=3, sig=False, normalize=False)[0]
+    assert np.abs(wct - ref).max() <= 1e-9
+
+
+def test_filterbanks_on_tiny_series(shim):
+    rng = np.random.default_rng(2)
+    for name in ("haar", "db2", "sym4"):
+        w = pw.Wavelet(name)
+        lo, hi = np.array(w.dec_lo), np.array(w.dec_hi)
+        for n in (1, 2, 3, 7, 9):
+            x = rng.standard_normal(n)
+            for J in (1, 4):
+                ref = mo.modwt(x, name, J)
+                got = shim.modwt(x, lo, hi, J, f64=True)
+                assert got.shape == (J + 1, n) and np.abs(got - ref).max() <= 1e-12, (name, n, J)
+                assert np.abs(shim.imodwt(got, lo, hi, f64=True) - x).max() <= 1e-10
+                assert np.abs(shim.modwtmra_taps(got, lo, hi, f64=True) - mo.modwtmra(ref, name)).max() <= 1e-10
+        for n in (len(lo), len(lo) + 1, 2 * len(lo) + 1):       # level 1 with a one-or-two sample overhang
+            x = rng.standard_normal(n)
+            packed, lens = shim.wavedec(x, lo, hi, 1, f64=True)
+            ref = pw.wavedec(x, name, level=1)
+            assert list(lens) == [c.size for c in ref] and np.abs(packed - np.concatenate(ref)).max() <= 1e-12
+            rec = shim.waverec(packed, lens, np.array(w.rec_lo), np.array(w.rec_hi), f64=True)
+            assert np.abs(rec - pw.waverec(ref, name)).max() <= 1e-12
+        packed, lens = shim.wavedec(rng.standard_normal(5), lo, hi, 0, f64=True)     # level 0: identity
+        assert list(lens) == [5]
+
+
+def test_rowwise_ols_minimum_and_constant_rows(shim):
+    x = np.array([[0.0, 1.0, 2.0], [1.0, 1.0, 1.0]])
+    y = np.array([[1.0, 3.0, 5.0], [2.0, 4.0, 6.0]])
+    st = shim.rowwise_ols(x, y, f64=True)
+    assert st[0, 1] == pytest.approx(1.0) and st[0, 2] == pytest.approx(2.0) and st[0, 3] == pytest.approx(0.0, abs=1e-24)
+    assert not np.isfinite(st[1, 2])                    # a constant regressor has no slope (statsmodels: nan / inf)
+    with pytest.raises(ValueError):
+        shim.rowwise_ols(x[:, :2], y[:, :2])
+    with pytest.raises(ValueError):
+        shim.rowwise_ols(x, y[:, :2])
+
+
+def test_icwt_single_scale_and_bad_shapes(shim):
+    W = (np.arange(6) + 1j).reshape(1, 6)
+    out = shim.icwt(W, np.array([4.0]), 2.0, f64=True)
+    assert np.allclose(out, 2.0 * np.arange(6) / 2.0)
+    with pytest.raises(ValueError):
+        shim.icwt(W, np.array([1.0, 2.0]), 1.0)
+
+
+def test_ragged_batches_by_length(shim):
+    """The engine's batches are rectangular; ragged collections go through one call per length
+    (api/regression._rowwise does the same).  Results must equal per-series calls."""
+    rng = np.random.default_rng(3)
+    series = [rng.standard_normal(n) for n in (64, 100, 64, 37, 100, 64)]
+    lo, hi = np.array(pw.Wavelet("sym4").dec_lo), np.array(pw.Wavelet("sym4").dec_hi)
+    by_len = {}
+    for i, s in enumerate(series):
+        by_len.setdefault(s.size, []).append(i)
+    out = [None] * len(series)
+    for n, idx in by_len.items():
+        w = shim.modwt(np.stack([series[i] for i in idx]), lo, hi, 2, f64=True)
+        for k, i in enumerate(idx):
+            out[i] = w[k]
+    for s, w in zip(series, out):
+        assert np.abs(w - mo.modwt(s, "sym4", 2)).max() <= 1e-12

@@ -155,3 +155,22 @@ def test_icwt_and_mother_names(shim, series):
     sj4 = wavelet.cwt(x, DT, 1 / 4, -1, -1, "dog")[1]
     out = shim.icwt(batch, sj4, 1.0, f64=True)                                       # batched entry point
     assert np.allclose(out[1], 2 * out[0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("n0,batch", [(4096, 2), (3351, 3), (2049, 1)])
+def test_cwt_fp32_nfft4096_register_rows(shim, n0, batch):
+    """Series of 2049..4096 samples take the radix-16 register-FFT rows (two series per CTA in
+    the two FFMA2 lanes; an odd batch ends with a half-empty CTA): oracle and generic parity."""
+    rng = np.random.default_rng(n0)
+    x = rng.standard_normal((batch, n0))
+    dj, J = 1 / 8, 65
+    power, coef = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, want_power=True, want_coef=True)
+    gen, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, generic_only=True)
+    assert power.shape == (batch, J + 1, n0) and coef.shape == power.shape
+    for b in range(batch):
+        W = po.cwt(x[b], DT, dj, 2 * DT, J, po.Morlet(6))[0]
+        ok, err = normwise_close(power[b], np.abs(W) ** 2, 1e-4)
+        assert ok, err
+        assert np.abs(coef[b] - W).max() <= 1e-4 * np.abs(W).max()
+        ok, err = normwise_close(power[b], gen[b], 1e-4)
+        assert ok, err

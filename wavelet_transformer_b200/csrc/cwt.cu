@@ -11,6 +11,10 @@ namespace wtb {
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
                  double f0, int flags, float *d_power, cudaStream_t st);
 
+// implemented in wct_fast.cu (register-FFT rows for nfft = 4096); returns 1 when not covered
+int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
+                      int flags, float *d_power, float2 *d_coef, cudaStream_t st);
+
 // One CTA = one (series, chunk of scales).  smem: 2 * N complex.
 template <typename T>
 __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
@@ -99,6 +103,13 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
   WTB_LAUNCH_CHECK();
+  if constexpr (sizeof(T) == 4) {
+    if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY)) {
+      const int rc = cwt_rows_4096_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power,
+                                       (float2 *)d_coef, st);
+      if (rc != 1) return rc;
+    }
+  }
   // enough CTAs to fill the machine for small batches, few forward-FFT re-reads for large ones
   int chunk = S;
   const int64_t want = 4LL * sm_count();

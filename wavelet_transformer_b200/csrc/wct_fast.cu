@@ -202,6 +202,61 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
   }
 }
 
+// Plain CWT rows for nfft = 4096 (series of 2049..4096 samples): round 1 of kernel A on its own,
+// with the two FFMA2 lanes carrying TWO SERIES instead of the two members of a pair.
+// xhat: [batch, 4096]; outputs (either may be null): power / coef [batch, S, n0].
+__global__ void __launch_bounds__(kThreads, 3)
+k_cwt_rows_4096(const float2 *__restrict__ xhat, int64_t batch, int n0, int S, const WRow *__restrict__ rows,
+                const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
+                float *__restrict__ power, float2 *__restrict__ coef) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *Bre = reinterpret_cast<float2 *>(smem_raw);
+  float2 *Bim = Bre + kBuf;
+  float2 *tw2s = Bim + kBuf;
+  const int j = threadIdx.x;
+  tw2s[j] = tw2[j];
+  const int64_t row = blockIdx.x;
+  const int64_t b0 = 2 * (row / S);
+  const int s = (int)(row % S);
+  const bool second = b0 + 1 < batch;       // an odd batch ends with a half-empty CTA
+  const WRow rp = rows[s];
+  const float2 *x1 = xhat + b0 * (int64_t)kN;
+  const float2 *x2 = second ? x1 + kN : x1;
+  float2 R[16], I[16];
+  {
+    const float zl = fmaf(rp.a, (float)j, -f0);
+    const float a256 = rp.a * 256.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < rp.R1) {
+        const float z = fmaf(a256, (float)r, zl);
+        const float2 dgt = bc(ex2(fmaf(z * z, -0.72134752044f, rp.lognorm)));
+        const float2 p = __ldg(&x1[j + 256 * r]), q = __ldg(&x2[j + 256 * r]);
+        R[br4(r)] = mul2(make_float2(p.x, q.x), dgt);
+        I[br4(r)] = mul2(make_float2(p.y, q.y), dgt);
+      }
+    }
+  }
+  __syncthreads();   // tw2s visible
+  fft4096_inv2(R, I, rp.L1, Bre, Bim, tw2s, tw3, j);
+  const int64_t o1 = (b0 * S + s) * (int64_t)n0, o2 = o1 + (int64_t)S * n0;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int t = j + 256 * r;
+    if (t < n0) {
+      if (coef) {
+        coef[o1 + t] = make_float2(R[r].x, I[r].x);
+        if (second) coef[o2 + t] = make_float2(R[r].y, I[r].y);
+      }
+      if (power) {
+        const float2 pw = fma2(R[r], R[r], mul2(I[r], I[r]));
+        __stcs(power + o1 + t, pw.x);
+        if (second) __stcs(power + o2 + t, pw.y);
+      }
+    }
+  }
+}
+
 // Kernel C: scale-axis boxcar of Morlet.smooth applied to the filtered spectra, in place.
 // One thread owns one frequency bin of one pair and slides over the scales with a ring of
 // the last K input rows in shared memory (column-private, so in-place is safe): every
@@ -432,22 +487,15 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
 
 }  // namespace
 
-// d_rows_scratch: device scratch for S WRow entries (caller's arena); d_spec: scratch of
-// pairs*S*4096 float4-equivalents.  Returns 1 when the shape is not covered.
-int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax, double f0,
-                 void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_spec, const ScaleWin &win,
-                 float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
-                 const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st) {
+static void fill_rows(const Axes &ax, double dt, double f0, std::vector<WRow> *rows) {
   const int S = ax.J + 1;
-  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32 || S > kMaxRowsC) return 1;
-  const bool smooth = d_wct || d_hist;
-  std::vector<WRow> rows(S);
+  rows->resize(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
     int khi = (int)std::floor((f0 + 5.3) / a);          // daughter < 8e-7 of its peak beyond
     if (khi > kN / 2 - 1) khi = kN / 2 - 1;
     if (khi < 1) khi = 1;
-    WRow &r = rows[s];
+    WRow &r = (*rows)[s];
     r.a = (float)a;
     r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / kN);
     r.gcoef = (float)(-0.5 * 1.4426950408889634 * a * a);
@@ -459,6 +507,48 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
     if (r.kc > kN / 2) r.kc = kN / 2;
     r.kc2 = (float)r.kc * (float)r.kc;   // kernel A stores exactly the bins kernel B reads
   }
+}
+
+// FP32 CWT rows for nfft = 4096 from forward spectra xhat [batch, 4096] (cwt.cu tries this
+// before its generic row kernel).  Returns 1 when the shape is not covered.
+int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
+                      int flags, float *d_power, float2 *d_coef, cudaStream_t st) {
+  const int S = ax.J + 1;
+  if (N != kN || f0 < 1.0 || (flags & WTB_COI_MASK) || S > kMaxRowsC) return 1;
+  std::vector<WRow> rows;
+  fill_rows(ax, dt, f0, &rows);
+  const float2 *tw2 = nullptr, *tw3 = nullptr;
+  WTB_TRY(ensure_tables(&tw2, &tw3));
+  // row parameters go to a small cached device buffer of their own (the caller's arena holds xhat)
+  static thread_local WRow *d_rows = nullptr;
+  static thread_local int d_rows_cap = 0;
+  if (d_rows_cap < S) {
+    if (d_rows) WTB_CUDA(cudaFree(d_rows));
+    WTB_CUDA(cudaMalloc(&d_rows, sizeof(WRow) * kMaxRowsC));
+    d_rows_cap = kMaxRowsC;
+  }
+  WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WRow) * S, cudaMemcpyHostToDevice, st));
+  const int64_t nrows = (batch + 1) / 2 * S;
+  WTB_REQUIRE(nrows < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+  const size_t smem = 2 * sizeof(float2) * kBuf + sizeof(float2) * 256;
+  WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cwt_rows_4096<<<(unsigned)nrows, kThreads, smem, st>>>(d_xhat, batch, n0, S, d_rows, tw2, tw3, (float)f0, d_power,
+                                                          d_coef);
+  WTB_LAUNCH_CHECK();
+  return WTB_OK;
+}
+
+// d_rows_scratch: device scratch for S WRow entries (caller's arena); d_spec: scratch of
+// pairs*S*4096 float4-equivalents.  Returns 1 when the shape is not covered.
+int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, const Axes &ax, double f0,
+                 void *d_rows_scratch, size_t rows_scratch_bytes, float4 *d_spec, const ScaleWin &win,
+                 float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
+                 const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st) {
+  const int S = ax.J + 1;
+  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32 || S > kMaxRowsC) return 1;
+  const bool smooth = d_wct || d_hist;
+  std::vector<WRow> rows;
+  fill_rows(ax, dt, f0, &rows);
   const float2 *tw2 = nullptr, *tw3 = nullptr;
   WTB_TRY(ensure_tables(&tw2, &tw3));
   WRow *d_rows = (WRow *)d_rows_scratch;

@@ -216,6 +216,19 @@ def run_gpu(args):
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local)
+    # Run this rank on the CPUs next to its GPU before any pinned host buffer is allocated: the
+    # host-buffer (e2e) arm is a PCIe stream per rank, and first-touch places its staging memory
+    # on the NUMA node the thread runs on.
+    numa = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        numa = sorted(os.sched_getaffinity(0))
+        numa = f"{numa[0]}-{numa[-1]} ({len(numa)} cpus)"
+    except Exception as exc:  # containers without the affinity interface: keep the default placement
+        numa = f"unchanged ({type(exc).__name__})"
     _shim.init(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -317,7 +330,7 @@ def run_gpu(args):
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * Be * S * n0 * args.e2e_steps / e2e_s, "unit": unit,
                "h2d_bytes_per_step": 4 * Be * n0, "d2h_bytes_per_step": 4 * Be * S * n0,
-               "series_per_step": Be, "steps": args.e2e_steps,
+               "series_per_step": Be, "steps": args.e2e_steps, "rank0_cpu_affinity": numa,
                "path": "wtb_cwt_morlet with pinned HOST buffers; H2D, kernels and D2H inside the timed region"}
         del xh, ph
     else:

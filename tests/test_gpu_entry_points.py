@@ -229,3 +229,51 @@ def test_cwt_batch_resident(shim, series):
         ratio = got / out["signif"][b].cpu().numpy()[:, None]
         assert np.abs(ratio - ref.significance_levels).max() <= 1e-8 * ref.significance_levels.max()
         assert float(out["ar1"][b]) == pytest.approx(po.ar1(xb)[0], rel=1e-10)
+
+
+def test_transform_helpers_batch_measures(series):
+    """create_*_results_dict (transform_helpers.py:89-140): measures of equal shape share one
+    launch; every entry must equal the reference's per-measure loop (run_dwt / wavedec / run_cwt /
+    run_xwt one at a time), mixed lengths and levels included."""
+    import pandas as pd
+    from src import cwt, dwt, xwt
+    from src.utils import transform_helpers as th
+    rng = np.random.default_rng(12)
+    infl, expn = series["inflation_value"], series["expectation_value"]
+    n = expn.size
+    growth = 100 * np.diff(np.log(series["cpi_value"]))      # AR(1)-bounded, unlike the raw inflation series
+    cols = {"infl": growth[-n:], "expn": expn, "noise": rng.standard_normal(n).cumsum()}
+    frame = pd.DataFrame({"date": np.arange(n).astype("datetime64[M]"), **cols})
+    # DWT: three equal-length measures + one shorter one + one with levels=None
+    ddict = th.create_dwt_dict(frame, list(cols))
+    ddict["short"] = dwt.DataForDWT(infl[:301], dwt.MOTHER, 4)
+    ddict["auto"] = dwt.DataForDWT(expn, dwt.MOTHER, None)
+    names = list(ddict)
+    plain = th.create_dwt_results_dict(ddict, names)
+    regr = th.create_dwt_regression_dict(ddict, names)
+    for m in names:
+        ref = pw.wavedec(ddict[m].y_values, "db4", level=ddict[m].levels)
+        one = dwt.run_dwt(ddict[m])
+        assert plain[m].levels == ddict[m].levels and regr[m].levels == one.levels
+        for got in (plain[m].coeffs, regr[m].coeffs):
+            assert [c.size for c in got] == [c.size for c in ref]
+            assert max(np.abs(g - r).max() for g, r in zip(got, ref)) <= 1e-12
+            assert all(np.array_equal(g, o) for g, o in zip(got, one.coeffs))
+    # CWT: batched launch vs run_cwt one by one (the bounded-AR(1) series of the app)
+    kw = dict(mother_wavelet=cwt.MOTHER, delta_t=cwt.DT, delta_j=cwt.DJ, initial_scale=cwt.S0, levels=cwt.LEVELS)
+    cdict = th.create_cwt_dict(frame, ["infl", "expn"], **kw)
+    cdict["short"] = cwt.DataForCWT(frame["date"].to_numpy()[:300], cols["expn"][:300], **kw)
+    cres = th.create_cwt_results_dict(cdict, ["short", "infl", "expn"], standardize=True, detrend=True)
+    assert list(cres) == ["short", "infl", "expn"]
+    for m, got in cres.items():
+        one = cwt.run_cwt(cdict[m], standardize=True, detrend=True)
+        assert got.power.shape == one.power.shape == (85, cdict[m].y_values.size)
+        assert np.abs(got.power - one.power).max() <= 1e-10 * one.power.max()
+        assert np.abs(got.significance_levels - one.significance_levels).max() <= 1e-9 * one.significance_levels.max()
+        assert np.array_equal(got.period, one.period) and np.array_equal(got.coi, one.coi)
+    assert th.create_cwt_results_dict(cdict, ["infl"], calculate_significance=False)["infl"].significance_levels is None
+    # XWT: the per-comparison loop
+    xdict = th.create_xwt_dict(frame, [("infl", "expn")])
+    xres = th.create_xwt_results_dict(xdict, [("infl", "expn")])
+    one = xwt.run_xwt(xdict[("infl", "expn")])
+    assert np.array_equal(xres[("infl", "expn")].power, one.power)

@@ -109,7 +109,7 @@ def test_imodwt_tma_path_many_ctas(shim, f64):
 
 # ---- register-blocked kernels (csrc/filterbank_fast.cu) vs the generic ones and the oracle ----
 @pytest.mark.parametrize("name", ["haar", "db2", "db3", "db4", "sym4"])
-@pytest.mark.parametrize("n,J", [(23, 6), (64, 4), (565, 6), (1000, 7), (1333, 6), (4096, 9)])
+@pytest.mark.parametrize("n,J", [(23, 6), (64, 4), (565, 6), (1000, 7), (1333, 6), (2048, 6), (3001, 7), (4096, 9)])
 def test_modwt_blocked_kernels_fp64(shim, name, n, J):
     """Chains of 9 outputs at stride 2^(j-1): aligned (TMA) and odd (cooperative) rows, tails that
     do not fill a chain, and dilated filters longer than the series (n=23, J=6)."""

@@ -218,3 +218,29 @@ def test_c_abi_demo_matches_python(tmp_path):
     w = mo.modwt(x, "sym4", 4)
     assert float(fields["modwt_energy_ratio"]) == pytest.approx((w ** 2).sum() / (x ** 2).sum(), abs=1e-10)
     assert float(fields["imodwt_err"]) < 1e-10 and int(fields["launches"]) >= 4
+
+
+def test_transform_helper_builders(series, shim_nogpu):
+    """create_dwt_dict / create_cwt_dict / create_xwt_dict (transform_helpers.py:21-86): host glue
+    from DataFrame columns to the dataclasses, NaN handling and the XWT constants included."""
+    import pandas as pd
+    from src import cwt, dwt, xwt
+    from src.utils import transform_helpers as th
+    from src.utils.wavelet_helpers import standardize_series
+    n = 120
+    rng = np.random.default_rng(4)
+    a, b = rng.standard_normal(n).cumsum(), rng.standard_normal(n)
+    b_nan = b.copy()
+    b_nan[:7] = np.nan
+    frame = pd.DataFrame({"date": np.arange(n).astype("datetime64[M]"), "a": a, "b": b_nan})
+    d = th.create_dwt_dict(frame.dropna(), ["a", "b"])
+    assert set(d) == {"a", "b"} and d["a"].mother_wavelet is dwt.MOTHER
+    assert d["a"].levels == shim_nogpu.dwt_max_level(n - 7, 8) and d["a"].y_values.size == n - 7
+    c = th.create_cwt_dict(frame, ["a", "b"], mother_wavelet=cwt.MOTHER, delta_t=cwt.DT, delta_j=cwt.DJ,
+                           initial_scale=cwt.S0, levels=cwt.LEVELS)
+    assert c["a"].y_values.size == n and c["b"].y_values.size == n - 7 == c["b"].t_values.size
+    assert np.array_equal(c["b"].y_values, standardize_series(b[7:]))
+    x = th.create_xwt_dict(frame, [("a", "b")], detrend=False, remove_mean=True)
+    item = x[("a", "b")]
+    assert item.y1_values.size == n - 7 and np.array_equal(item.y2_values, standardize_series(b[7:], detrend=False, remove_mean=True))
+    assert (item.delta_t, item.delta_j, item.initial_scale) == (xwt.DT, xwt.DJ, xwt.S0) and item.levels == xwt.LEVELS

@@ -12,6 +12,7 @@ from typing import List, Type
 import numpy as np
 import numpy.typing as npt
 
+from .. import _shim
 from .. import pycwt_compat as wavelet
 from .wavelet_helpers import standardize_series
 
@@ -74,3 +75,33 @@ def run_cwt(cwt_data: Type[DataForCWT], normalize: bool = True, standardize: boo
                                          wavelet=cwt_data.mother_wavelet)
         ratio = power / (np.ones([1, len(cwt_data.t_values)]) * signif[:, None])
     return ResultsFromCWT(power, period, ratio, coi)
+
+
+def run_cwt_batch(cwt_data_list: List[Type[DataForCWT]], normalize: bool = True, standardize: bool = False,
+                  calculate_significance: bool = True, significance_level: float = 0.95,
+                  **kwargs) -> List[Type[ResultsFromCWT]]:
+    """``run_cwt`` of several equal-length Morlet series as ONE fused CWT+power launch
+    (the loop of src/utils/transform_helpers.py:117-124 as a batch).  Per series the result
+    equals ``run_cwt``'s; ``ar1`` still raises ``Warning`` for a series it cannot bound."""
+    if not cwt_data_list:
+        return []
+    mother = wavelet._as_mother(cwt_data_list[0].mother_wavelet)
+    ys = [np.asarray(d.y_values, dtype=float) for d in cwt_data_list]
+    if len({y.size for y in ys}) != 1:
+        raise ValueError("run_cwt_batch takes series of equal length")
+    alphas = [wavelet.ar1(y)[0] for y in ys]
+    signals = np.stack([standardize_series(y, **kwargs) if standardize else y for y in ys])
+    n0 = signals.shape[1]
+    _, scales, freqs, coi = wavelet._resolve_s0_J(n0, DT, DJ, S0, J, mother)
+    power, _ = _shim.cwt_morlet(signals, DT, DJ, S0, int(J), mother.f0, f64=True)
+    power = np.asarray(power, dtype=float).reshape(len(ys), scales.size, n0)
+    period = 1 / freqs
+    out = []
+    for b, (d, alpha) in enumerate(zip(cwt_data_list, alphas)):
+        ratio = None
+        if calculate_significance:
+            signif, _ = wavelet.significance(1.0, DT, scales, 0, alpha, significance_level=significance_level,
+                                             wavelet=mother)
+            ratio = power[b] / (np.ones([1, len(d.t_values)]) * signif[:, None])
+        out.append(ResultsFromCWT(power[b], period.copy(), ratio, coi.copy()))
+    return out

@@ -9,6 +9,7 @@ from typing import Dict, Type
 import numpy as np
 import numpy.typing as npt
 
+from .. import _shim
 from .. import pywt_compat as pywt
 
 logger = logging.getLogger(__name__)
@@ -47,12 +48,22 @@ class ResultsFromDWT:
         """For l = levels..1 zero the l finest detail blocks and reconstruct;
         entry l holds the signal with detail levels <= l removed."""
         out = {}
-        for l in range(self.levels, 0, -1):
+        w = mother_wavelet if hasattr(mother_wavelet, "rec_lo") else pywt.Wavelet(mother_wavelet)
+        parts = [np.asarray(c, dtype=float).ravel() for c in self.coeffs]
+        lens = np.array([p.size for p in parts], dtype=np.int32)
+        edges = np.concatenate([[0], np.cumsum(lens)])
+        order = list(range(self.levels, 0, -1))
+        packed = np.tile(np.concatenate(parts), (len(order), 1))
+        for row, l in enumerate(order):                       # zero the l finest detail blocks
+            packed[row, edges[len(parts) - l]:] = 0.0
+        # every smoothing level in ONE batched reconstruction launch
+        recs = (np.asarray(_shim.waverec(packed, lens, w.rec_lo, w.rec_hi, f64=True), dtype=float)
+                if len(parts) > 1 else packed)
+        for row, l in enumerate(order):
             kept = list(self.coeffs)
             for c in range(1, l + 1):
                 kept[-c] = np.zeros_like(kept[-c])
-            rec = pywt.waverec(kept, mother_wavelet)
-            out[l] = {"coeffs": kept, "signal": trim_signal(y_values, rec)}
+            out[l] = {"coeffs": kept, "signal": trim_signal(y_values, recs[row])}
         self.smoothed_signal_dict = out
 
 

@@ -22,6 +22,10 @@
 namespace wtb {
 
 constexpr int kRM = 9;         // MODWT outputs per thread
+constexpr int kRA = 17;        // MRA cascade outputs per thread for long rows (n >= kLongRow): the one-filter
+                               // passes are bound by shared-memory wavefronts and a longer chain reads
+                               // (R+L-1)/R per output; short rows keep kRM so a CTA still has >= 4 warps
+constexpr int kLongRow = 2048;
 constexpr int kRD = 5;         // DWT outputs (analysis) / output pairs (synthesis) per thread
 constexpr int kMaxFastJ = 10;  // a-trous levels with a compile-time dilation (d <= 512)
 constexpr int kChainThreads = 512;  // CTA size limit of the a-trous kernels (<= 64 registers per thread)
@@ -357,10 +361,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_imodwt_blk(const T *__rest
 // synthesis step at dilation 2^(k-1).  Algebraically this is the reference's correlation with
 // the periodised equivalent filter (src/modwt.py:163-194), at sum_j j*L instead of
 // sum_j ((2^j - 1)(L-1) + 1) multiply-adds per sample.
-template <typename T, int L, int SH, bool HI>
+template <typename T, int L, int R, int SH, bool HI>
 __device__ __forceinline__ void cascade_level(T *__restrict__ a, int n, int mirror, const TapsK<T, L> &tp,
                                            const Chain ch) {
-  constexpr int R = kRM, d = 1 << SH;
+  constexpr int d = 1 << SH;
   T acc[R];
   {
 #pragma unroll
@@ -380,7 +384,7 @@ __device__ __forceinline__ void cascade_level(T *__restrict__ a, int n, int mirr
   if (ch.active) store_chain<T, R, d>(a, acc, ch.t0, n, mirror);
 }
 
-template <typename T, int L>
+template <typename T, int L, int R>
 __global__ void __launch_bounds__(kChainThreads, 2) k_mra_blk(const T *__restrict__ w, int n, int J, TapsK<T, L> tp, T *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
@@ -400,14 +404,14 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_mra_blk(const T *__restric
   for (int k = lev; k >= 1; --k) {
     const int mirror = k > 1 ? halo_of(L, k - 2) : 0;
     const bool first = k == lev && row < J;  // the detail rows enter through the wavelet filter
-    const Chain ch(n, k - 1, kRM);
+    const Chain ch(n, k - 1, R);
     switch (k - 1) {
 #define WTB_LEVEL(SH)                                              \
   case SH:                                                         \
     if (first)                                                     \
-      cascade_level<T, L, SH, true>(a, n, mirror, tp, ch);         \
+      cascade_level<T, L, R, SH, true>(a, n, mirror, tp, ch);         \
     else                                                           \
-      cascade_level<T, L, SH, false>(a, n, mirror, tp, ch);        \
+      cascade_level<T, L, R, SH, false>(a, n, mirror, tp, ch);        \
     break;
       WTB_LEVEL(0) WTB_LEVEL(1) WTB_LEVEL(2) WTB_LEVEL(3) WTB_LEVEL(4)
       WTB_LEVEL(5) WTB_LEVEL(6) WTB_LEVEL(7) WTB_LEVEL(8) WTB_LEVEL(9)
@@ -590,11 +594,11 @@ static int round_threads(int64_t items) {
 // CTA size for the a-trous kernels: one chain per thread at every level.  0 = not coverable:
 // too many levels for the compile-time dilations, a dilated filter longer than the series
 // (the halo would wrap more than once), or more chains than a CTA has threads.
-static int chain_threads(int n, int L, int J) {
+static int chain_threads(int n, int L, int J, int R = kRM) {
   if (J > kMaxFastJ || halo_of(L, J - 1) > n) return 0;
   int64_t most = 0;
   for (int j = 1; j <= J; ++j) {
-    const int64_t d = int64_t(1) << (j - 1), span = d * kRM;
+    const int64_t d = int64_t(1) << (j - 1), span = d * R;
     most = std::max<int64_t>(most, ((n + span - 1) / span) * d);
   }
   return most <= kChainThreads ? round_threads(most) : 0;
@@ -632,20 +636,29 @@ int imodwt_fast(const void *w, int64_t batch, int n, const Taps &taps, int J, vo
   return WTB_OK;
 }
 
-template <typename T>
-int mra_fast(const void *w, int64_t batch, int n, const Taps &taps, int J, void *out, cudaStream_t st) {
-  if (!fast_taps_ok(taps.L) || batch * (J + 1) >= (1LL << 31)) return WTB_EUNSUPPORTED;
-  const int threads = chain_threads(n, taps.L, J);
+template <typename T, int R>
+static int mra_fast_r(const void *w, int64_t batch, int n, const Taps &taps, int J, void *out, cudaStream_t st) {
+  const int threads = chain_threads(n, taps.L, J, R);
   if (!threads) return WTB_EUNSUPPORTED;
-  const size_t smem = sizeof(T) * (size_t)((n + (kRM + taps.L - 2) * (1 << (J - 1)) + 4 + 3) & ~3);
+  const size_t smem = sizeof(T) * (size_t)((n + (R + taps.L - 2) * (1 << (J - 1)) + 4 + 3) & ~3);
   if (smem > kSmemLimit) return WTB_EUNSUPPORTED;
   WTB_TAPS_SWITCH(taps.L, {
-    WTB_TRY(set_smem(k_mra_blk<T, LT>, smem));
-    k_mra_blk<T, LT><<<(unsigned)(batch * (J + 1)), threads, smem, st>>>((const T *)w, n, J, narrow_taps<T, LT>(taps),
-                                                                        (T *)out);
+    WTB_TRY(set_smem(k_mra_blk<T, LT, R>, smem));
+    k_mra_blk<T, LT, R><<<(unsigned)(batch * (J + 1)), threads, smem, st>>>((const T *)w, n, J,
+                                                                           narrow_taps<T, LT>(taps), (T *)out);
   });
   WTB_LAUNCH_CHECK();
   return WTB_OK;
+}
+
+template <typename T>
+int mra_fast(const void *w, int64_t batch, int n, const Taps &taps, int J, void *out, cudaStream_t st) {
+  if (!fast_taps_ok(taps.L) || batch * (J + 1) >= (1LL << 31)) return WTB_EUNSUPPORTED;
+  if (n >= kLongRow) {
+    const int rc = mra_fast_r<T, kRA>(w, batch, n, taps, J, out, st);
+    if (rc != WTB_EUNSUPPORTED) return rc;   // e.g. the longer chains' halo no longer fits
+  }
+  return mra_fast_r<T, kRM>(w, batch, n, taps, J, out, st);
 }
 
 template <typename T>

@@ -277,3 +277,48 @@ def test_transform_helpers_batch_measures(series):
     xres = th.create_xwt_results_dict(xdict, [("infl", "expn")])
     one = xwt.run_xwt(xdict[("infl", "expn")])
     assert np.array_equal(xres[("infl", "expn")].power, one.power)
+
+
+def test_entry_points_are_reentrant_across_host_threads(shim, series):
+    """SURVEY 8b threading: several Streamlit sessions are several host threads in one process.
+    ctypes releases the GIL, so the calls below really overlap; every thread has its own scratch
+    arena and error slot, and each result must equal the one computed alone."""
+    import threading
+    from wavelet_transformer_b200 import pywt_compat as pywt
+    rng = np.random.default_rng(77)
+    la8 = pywt.Wavelet("sym4")
+    x32 = rng.standard_normal((64, 1024))
+    x64 = rng.standard_normal((3, 700))
+    y1, y2 = series["pair_inflation"], series["pair_expectation"]
+    n1, n2 = (y1 - y1.mean()) / y1.std(), (y2 - y2.mean()) / y2.std()
+    jobs = {
+        "cwt32": lambda: shim.cwt_morlet(x32, DT, 1 / 12, 2 * DT, 119, f64=False)[0],
+        "cwt64": lambda: shim.cwt_morlet(x64, DT, 1 / 12, 2 * DT, 60, f64=True)[0],
+        "wct": lambda: shim.xwt_wct(n1, n2, DT, 1 / 8, 2 * DT, -1, f64=True)[0],
+        "modwt": lambda: shim.modwtmra_taps(shim.modwt(x64, la8.dec_lo, la8.dec_hi, 6, f64=True),
+                                            la8.dec_lo, la8.dec_hi, f64=True),
+        "dwt": lambda: shim.wavedec(series["inflation_value"], la8.dec_lo, la8.dec_hi, 7, f64=True)[0],
+        "mc": lambda: shim.wct_mc_hist(0.8, 0.6, DT, 1 / 4, 2 * DT, 20, mc_count=16, seed=5, f64=False),
+    }
+    alone = {k: np.array(fn()) for k, fn in jobs.items()}
+    failures = []
+
+    def worker(name, fn):
+        try:
+            for _ in range(6):
+                if not np.array_equal(np.array(fn()), alone[name]):
+                    failures.append(f"{name}: result differs under concurrency")
+                    return
+        except Exception as exc:   # noqa: BLE001 - reported below
+            failures.append(f"{name}: {exc!r}")
+
+    threads = [threading.Thread(target=worker, args=item) for item in jobs.items()]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in threads), "a worker thread hung"
+    assert not failures, failures
+    # an error raised in one thread carries that thread's own message
+    with pytest.raises(Exception, match="power of two"):
+        shim.cwt_morlet(x64, DT, 1 / 12, 2 * DT, 10, nfft=1000, f64=True)

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the fused CWT+power paths by series shape, against the HBM roofline.
+
+    python tools/bench_cwt_shapes.py
+
+Unit = one series; algorithmic bytes 4*n0*(1 + S) (FP32 series in, power plane out).  Shapes: BASELINE
+cfg1 (1346 samples -> nfft 2048, 85 scales), full 2048, cfg4 (1024 x 120) and the nfft-4096 rows;
+each also through the generic Stockham kernel for reference.
+"""
+
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    import torch
+
+    from wavelet_transformer_b200 import _shim
+
+    _shim.init(0)
+    peaks = ROOT / "MEASURED_PEAKS.json"
+    peak = json.loads(peaks.read_text())["hbm_gbs"] if peaks.exists() else 6650.0
+    dev = torch.device("cuda", 0)
+    dt = 1 / 12
+    shapes = [("cfg1 shape", 1346, 1 / 12, 84, 20000), ("nfft 2048 full", 2048, 1 / 12, 84, 20000),
+              ("odd rows", 1345, 1 / 12, 84, 20000), ("cfg4", 1024, 1 / 12, 119, 20000),
+              ("nfft 4096", 3351, 1 / 8, 65, 4000)]
+    for label, n0, dj, J, batch in shapes:
+        S = J + 1
+        x = torch.randn((batch, n0), dtype=torch.float32, device=dev)
+        out = torch.empty((batch, S, n0), dtype=torch.float32, device=dev)
+        for generic in (False, True):
+            nb = batch if not generic else batch // 4
+
+            def step():
+                _shim.cwt_power_device(x.data_ptr(), nb, n0, dt, dj, 2 * dt, J, 6.0, out.data_ptr(), f64=False,
+                                       generic_only=generic)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3 / 5
+            gbs = 4.0 * n0 * (1 + S) * nb / t / 1e9
+            print(json.dumps({"shape": label, "n0": n0, "scales": S, "batch": nb, "kernel": "generic" if generic else "fast",
+                              "ms": t * 1e3, "coeff_per_s": nb * S * n0 / t, "achieved_GBs": gbs, "frac_hbm": gbs / peak}))
+        del x, out
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,10 @@ namespace wtb {
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
                  double f0, int flags, float *d_power, cudaStream_t st);
 
+// implemented in cwt_fast.cu (two interleaved 1024-point passes per row for nfft = 2048); 1 = not covered
+int cwt_fast_2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
+                      int flags, float *d_power, cudaStream_t st);
+
 // implemented in wct_fast.cu (register-FFT rows for nfft = 4096); returns 1 when not covered
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, float2 *d_coef, cudaStream_t st);
@@ -104,6 +108,10 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
   WTB_LAUNCH_CHECK();
   if constexpr (sizeof(T) == 4) {
+    if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef) {
+      const int rc = cwt_fast_2048_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
+      if (rc != 1) return rc;
+    }
     if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY)) {
       const int rc = cwt_rows_4096_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power,
                                        (float2 *)d_coef, st);

@@ -102,7 +102,8 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
   for (int i = threadIdx.x; i < S; i += blockDim.x) sm.row[i] = rows[i];
   __syncthreads();
   WarpSmem &ws = sm.w[warp];
-  const int64_t gwarp = (int64_t)blockIdx.x * kWarps + warp;
+  // consecutive series go to different SMs: a small batch spreads over the machine
+  const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
   const bool full_row = (n0 == kN);
   const float lanef = (float)lane;
@@ -438,8 +439,7 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
     constexpr int W = decltype(tag)::value;
     const size_t smem = sizeof(CtaSmem<W>);
     WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ctas_needed = (batch + W - 1) / W;
-    const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count());
+    const int grid = (int)std::min<int64_t>(batch, (int64_t)sm_count());
     k_cwt_fast_1024<W><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
     WTB_LAUNCH_CHECK();
     return WTB_OK;

@@ -179,10 +179,10 @@ def test_cwt_fp32_nfft4096_register_rows(shim, n0, batch):
 @pytest.mark.parametrize("n0,dj,J", [(1346, 1 / 12, 84), (1345, 1 / 12, 84), (2048, 1 / 8, 70), (1025, 1 / 4, -1)])
 def test_cwt_fp32_nfft2048_interleaved_passes(shim, n0, dj, J):
     """Batches of 1025..2048-sample series (BASELINE cfg1's 1346-month CPI shape) take the
-    warp-autonomous kernel twice per row (even / odd output samples); even n0 stores (even, odd)
-    pairs, odd n0 scalars.  Oracle parity on sampled series, generic-kernel parity on all."""
+    warp-autonomous 1024-point kernel twice per row (even / odd output samples), even and odd
+    row lengths.  Oracle parity on sampled series, generic-kernel parity on all."""
     rng = np.random.default_rng(n0)
-    batch = 300                                   # >= the 256-series threshold of the fast path
+    batch = 300                                   # >= the 128-series threshold of the fast path
     x = rng.standard_normal((batch, n0)).cumsum(axis=1) * 0.05 + rng.standard_normal((batch, n0))
     power, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False)
     gen, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, generic_only=True)
@@ -197,3 +197,4 @@ def test_cwt_fp32_nfft2048_interleaved_passes(shim, n0, dj, J):
     # below the threshold the generic kernel serves the call: same numbers either way
     small, _ = shim.cwt_morlet(x[:5], DT, dj, 2 * DT, J, f64=False)
     assert np.array_equal(small, gen[:5])
+

@@ -12,7 +12,7 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
                  double f0, int flags, float *d_power, cudaStream_t st);
 
 // implemented in cwt_fast.cu (two interleaved 1024-point passes per row for nfft = 2048); 1 = not covered
-int cwt_fast_2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
+int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, cudaStream_t st);
 
 // implemented in wct_fast.cu (register-FFT rows for nfft = 4096); returns 1 when not covered
@@ -109,7 +109,7 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   WTB_LAUNCH_CHECK();
   if constexpr (sizeof(T) == 4) {
     if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef) {
-      const int rc = cwt_fast_2048_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
+      const int rc = cwt_fast_fold_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
       if (rc != 1) return rc;
     }
     if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY)) {

@@ -226,44 +226,46 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 
 
 // ---- nfft = 2048 (series of 1025..2048 samples, e.g. the reference's 1346-month CPI series) ----
-// The same warp-autonomous machinery run twice per scale row.  With N = 2 * 1024 and a
-// one-sided spectrum Y[k], k < 1024:
-//   x[2u]   = sum_k  Y[k]               w1024^(k u)      (phase 0)
-//   x[2u+1] = sum_k (Y[k] w2048^k)      w1024^(k u)      (phase 1)
-// i.e. two 1024-point inverse transforms of the same band, the second with a pre-twiddle.
-// Phase 0 parks its |w|^2 in registers, phase 1 interleaves the two and stores 8-byte
-// (even, odd) pairs: every warp store still writes whole 128-byte lines.  The forward
-// transform comes from k_fwd_fft (cwt.cu) as xhat [batch][2048]; the warp stages its positive
-// half in shared memory once per series.
-constexpr int kN2 = 2048;
-constexpr int kWarps2 = 12;           // 8 KB more shared memory per warp than the 1024 kernel
-constexpr int kMaxRows2 = 128;
-constexpr int kMinBatch2 = 256;
+// The same warp-autonomous 1024-point machinery run twice per scale row.  With N = 2 * 1024 and a
+// one-sided spectrum Y[k], k < 1024, the output samples t = 2u + q of phase q are
+//   x[2u + q] = sum_{k < 1024} (Y[k] w_N^(q k)) w1024^(k u):
+// two inverse transforms of the same band, the second with a pre-twiddle from a shared-memory
+// table.  Each phase stores its own samples at stride 2 (the two halves of a 128-byte line meet in
+// L2; DRAM traffic is unchanged.  Parking phase 0 in registers to store whole lines costs 50
+// registers and 4 warps: 3-8 % slower below ~1700 samples, 13 % faster at 2048).  The forward transform comes from k_fwd_fft (cwt.cu) as xhat [batch][N]; rows re-read
+// their band through L1 (__ldg), so shared memory holds only the transpose buffer and the tables:
+// 16 warps per SM like the 1024 kernel.
+// The 4-fold version of this for nfft = 4096 (samples 4u + q, bins 1024..2047 folded into each
+// pass) was built and measured at 2.7e11 coeff/s against 4.0e11 for the radix-16 register rows of
+// wct_fast.cu: its stride-4 stores turn every 32-byte sector into four 8-byte L2 write requests
+// and the L2 request rate becomes the limit.  It was dropped.
+constexpr int kMaxRowsF = 128;
+constexpr int kMinBatchF = 128;
 
-struct WarpSmem2 {
-  float2 xr[16][32];                // xr[m][lane] = Re X^[lane + 32*(2m)], Re X^[lane + 32*(2m+1)], bins < 1024
-  float2 xi[16][32];
+struct WarpSmemF {
   float trr[32 * kTrStride];        // transpose buffer; its first 32 floats double as Y[k] of a single-pass row
   float tri[32 * kTrStride];
 };
 
-struct CtaSmem2 {
+template <int D> struct CtaSmemF {
   float4 tw_a[16][32];              // as in CtaSmem: twiddles of the 1024-point transform
   float4 tw_b[16][32];
-  float4 tw_c[16][32];              // exp(+2*pi*i*k/2048) for the pair k = lane + 64 m, k + 32 : phase-1 pre-twiddle
-  RowParam row[kMaxRows2];
-  WarpSmem2 w[kWarps2];
+  float4 tw_c[D - 1][16][32];       // exp(+2*pi*i*q*k/N) for the pair k = lane + 64 m, k + 32, q = 1 .. D-1
+  RowParam row[kMaxRowsF];
+  WarpSmemF w[kWarpsDefault];
 };
 
 __device__ __forceinline__ constexpr int below_pow2_16(int m) {
   return m < 8 ? below_pow2(m) : 8;
 }
 
-__global__ void __launch_bounds__(kWarps2 * 32, 1)
-k_cwt_fast_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
+template <int D>
+__global__ void __launch_bounds__(kWarpsDefault * 32, 1)
+k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
                 const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
+  constexpr int kNF = kN * D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CtaSmem2 &sm = *reinterpret_cast<CtaSmem2 *>(smem_raw);
+  CtaSmemF<D> &sm = *reinterpret_cast<CtaSmemF<D> *>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
@@ -275,37 +277,30 @@ k_cwt_fast_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     sincospif(2.0f * (float)(2 * p * l) / (float)kN, &s0, &c0);
     sincospif(2.0f * (float)((2 * p + 1) * l) / (float)kN, &s1, &c1);
     sm.tw_b[p][l] = make_float4(c0, c1, s0, s1);
-    sincospif(2.0f * (float)(l + 64 * p) / (float)kN2, &s0, &c0);
-    sincospif(2.0f * (float)(l + 64 * p + 32) / (float)kN2, &s1, &c1);
-    sm.tw_c[p][l] = make_float4(c0, c1, s0, s1);
+#pragma unroll
+    for (int q = 1; q < D; ++q) {
+      sincospif(2.0f * (float)(q * (l + 64 * p)) / (float)kNF, &s0, &c0);
+      sincospif(2.0f * (float)(q * (l + 64 * p + 32)) / (float)kNF, &s1, &c1);
+      sm.tw_c[q - 1][p][l] = make_float4(c0, c1, s0, s1);
+    }
   }
   for (int i = threadIdx.x; i < S; i += blockDim.x) sm.row[i] = rows[i];
   __syncthreads();
-  WarpSmem2 &ws = sm.w[warp];
+  WarpSmemF &ws = sm.w[warp];
   float *const yr = ws.trr, *const yi = ws.tri;      // single-pass rows never touch the transpose buffer
   // consecutive series go to different SMs: a small batch spreads over the machine
   const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
-  const int64_t nwarps = (int64_t)gridDim.x * kWarps2;
-  const bool pairs_ok = (n0 & 1) == 0;               // rows start 8-byte aligned
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsDefault;
   const float lanef = (float)lane;
   const int tidx = 2 * (lane & 15) + (lane >> 4);
-  const float4 twl = sm.tw_c[0][lane];               // (cos, ., sin, .) of 2*pi*lane/2048
-  float2 R[16], I[16], keep[16];
+  float2 R[16], I[16];
 
   for (int64_t b = gwarp; b < batch; b += nwarps) {
-    const float2 *xh = xhat + b * kN2;
-    __syncwarp();                                    // the previous series' last row is done with X^
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const float2 v0 = __ldg(xh + lane + 64 * m), v1 = __ldg(xh + lane + 64 * m + 32);
-      ws.xr[m][lane] = make_float2(v0.x, v1.x);
-      ws.xi[m][lane] = make_float2(v0.y, v1.y);
-    }
-    __syncwarp();
-    float *out = power + b * (int64_t)S * n0;
+    const float2 *xh = xhat + b * kNF + lane;
+    float *out = power + b * (int64_t)S * n0 + D * lane;
 #pragma unroll 1
-    for (int sq = 0; sq < 2 * S; ++sq) {
-      const int s = sq >> 1, q = sq & 1;
+    for (int sq = 0; sq < D * S; ++sq) {
+      const int s = sq / D, q = sq % D;
       const RowParam rp = sm.row[s];
       const int L = rp.L, two_pass = rp.multi;
       const float zl = fmaf(rp.a, lanef, -f0);       // s*w_k - f0 at k = lane
@@ -320,9 +315,10 @@ k_cwt_fast_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
             const float2 z = fma2(a64, bc((float)m), zl2);
             const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);
             const float2 d = make_float2(ex2(e.x), ex2(e.y));
-            float2 vr = mul2(ws.xr[m][lane], d), vi = mul2(ws.xi[m][lane], d);
+            const float2 v0 = __ldg(xh + 64 * m), v1 = __ldg(xh + 64 * m + 32);
+            float2 vr = mul2(make_float2(v0.x, v1.x), d), vi = mul2(make_float2(v0.y, v1.y), d);
             if (q) {
-              const float4 t = sm.tw_c[m][lane];
+              const float4 t = sm.tw_c[q - 1][m][lane];
               const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
               const float2 ur = fma2(vi, neg2(twi), mul2(vr, twr));
               vi = fma2(vr, twi, mul2(vi, twr));
@@ -334,11 +330,12 @@ k_cwt_fast_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         }
       } else {
         const float d = ex2(fmaf(zl * zl, -0.72134752044f, rp.lognorm));
-        const float2 vr = ws.xr[0][lane], vi = ws.xi[0][lane];
-        float ar = vr.x * d, ai = vi.x * d;
+        const float2 v0 = __ldg(xh);
+        float ar = v0.x * d, ai = v0.y * d;
         if (q) {
-          const float ur = fmaf(-ai, twl.z, ar * twl.x);
-          ai = fmaf(ar, twl.z, ai * twl.x);
+          const float4 t = sm.tw_c[q - 1][0][lane];  // (cos, ., sin, .) of 2*pi*q*lane/N
+          const float ur = fmaf(-ai, t.z, ar * t.x);
+          ai = fmaf(ar, t.z, ai * t.x);
           ar = ur;
         }
         yr[lane] = ar;
@@ -378,26 +375,15 @@ k_cwt_fast_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         __syncwarp();
         fft32::dit32(R, I, 5);
       }
-      // position p holds u = lane + 32 p (.x) and u + 512 (.y); this phase is sample t = 2u + q
-      if (q == 0) {
+      // position p holds u = lane + 32 p (.x) and u + 512 (.y); this phase is sample t = D u + q.
+      // Default store policy: the other parts of the line follow within this row.
+      float *orow = out + (int64_t)s * n0 + q;
+      const int tl = D * lane + q;
 #pragma unroll
-        for (int p = 0; p < 16; ++p) keep[p] = fma2(R[p], R[p], mul2(I[p], I[p]));
-      } else {
-        float *orow = out + (int64_t)s * n0 + 2 * lane;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-          const int t0 = 2 * lane + 64 * p, t1 = t0 + 1024;
-          if (pairs_ok) {                            // n0 even: a pair is inside the row or outside it
-            if (t0 < n0) __stcs(reinterpret_cast<float2 *>(orow + 64 * p), make_float2(keep[p].x, pw.x));
-            if (t1 < n0) __stcs(reinterpret_cast<float2 *>(orow + 64 * p + 1024), make_float2(keep[p].y, pw.y));
-          } else {
-            if (t0 < n0) __stcs(orow + 64 * p, keep[p].x);
-            if (t0 + 1 < n0) __stcs(orow + 64 * p + 1, pw.x);
-            if (t1 < n0) __stcs(orow + 64 * p + 1024, keep[p].y);
-            if (t1 + 1 < n0) __stcs(orow + 64 * p + 1025, pw.y);
-          }
-        }
+      for (int p = 0; p < 16; ++p) {
+        const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+        if (tl + 32 * D * p < n0) orow[32 * D * p] = pw.x;
+        if (tl + 32 * D * p + 512 * D < n0) orow[32 * D * p + 512 * D] = pw.y;
       }
     }
   }
@@ -453,34 +439,35 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 }
 
 
-// FP32 CWT + power rows for nfft = 2048 from forward spectra xhat [batch, 2048] (cwt.cu tries
+// FP32 CWT + power rows for nfft = 2048 from forward spectra xhat [batch, nfft] (cwt.cu tries
 // this after its forward-FFT kernel).  Returns 1 when the shape is not covered.
-int cwt_fast_2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
+int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
-  // one warp walks all rows of a series: below a few series per SM the generic kernel, which
-  // spreads the scales of one series over CTAs, has the shorter critical path
-  if (nfft != kN2 || (flags & WTB_COI_MASK) || f0 < 1.0 || S > kMaxRows2 || batch < kMinBatch2) return 1;
+  // One warp walks all rows of a series: for a handful of series the generic kernel, which
+  // spreads the scales of one series over CTAs, has the shorter critical path (measured
+  // crossover below 128 series).
+  if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < 1.0 || S > kMaxRowsF || batch < kMinBatchF) return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
-    const double a = ax.scales[s] / dt * 2.0 * kPi / kN2;
+    const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;
     int khi = (int)std::floor((f0 + kZCut) / a);
-    khi = std::max(1, std::min(khi, kN2 / 2 - 1));
+    khi = std::max(1, std::min(khi, nfft / 2 - 1));
     RowParam &r = rows[s];
     r.a = (float)a;
-    r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / kN2);
+    r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / nfft);
     r.multi = khi >= 32;
     r.L = r.multi ? std::max(1, std::min(5, ilog2(khi / 32 + 1))) : ilog2(khi + 1);
   }
   // the caller's arena holds xhat: row parameters get a small cached buffer of their own
   static thread_local RowParam *d_rows = nullptr;
-  if (!d_rows) WTB_CUDA(cudaMalloc(&d_rows, sizeof(RowParam) * kMaxRows2));
+  if (!d_rows) WTB_CUDA(cudaMalloc(&d_rows, sizeof(RowParam) * kMaxRowsF));
   // rows.data() is pageable: the copy is staged before the call returns
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
-  const size_t smem = sizeof(CtaSmem2);
-  WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(batch, (int64_t)sm_count());
-  k_cwt_fast_2048<<<grid, kWarps2 * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, (float)f0, d_power);
+  const size_t smem = sizeof(CtaSmemF<2>);
+  WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_fold<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cwt_fast_fold<2><<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, (float)f0, d_power);
   WTB_LAUNCH_CHECK();
   return WTB_OK;
 }

@@ -10,6 +10,7 @@ each also through the generic Stockham kernel for reference.
 
 from __future__ import annotations
 
+import argparse
 import json
 import sys
 from pathlib import Path
@@ -23,6 +24,10 @@ def main():
 
     from wavelet_transformer_b200 import _shim
 
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, help="substring of the shape label to run (default: all)")
+    ap.add_argument("--no-generic", action="store_true")
+    args = ap.parse_args()
     _shim.init(0)
     peaks = ROOT / "MEASURED_PEAKS.json"
     peak = json.loads(peaks.read_text())["hbm_gbs"] if peaks.exists() else 6650.0
@@ -32,10 +37,12 @@ def main():
               ("odd rows", 1345, 1 / 12, 84, 20000), ("cfg4", 1024, 1 / 12, 119, 20000),
               ("nfft 4096", 3351, 1 / 8, 65, 4000)]
     for label, n0, dj, J, batch in shapes:
+        if args.only and args.only not in label:
+            continue
         S = J + 1
         x = torch.randn((batch, n0), dtype=torch.float32, device=dev)
         out = torch.empty((batch, S, n0), dtype=torch.float32, device=dev)
-        for generic in (False, True):
+        for generic in ((False,) if args.no_generic else (False, True)):
             nb = batch if not generic else batch // 4
 
             def step():

@@ -255,6 +255,17 @@ template <int D> struct CtaSmemF {
   WarpSmemF w[kWarpsDefault];
 };
 
+// X^ is the only data a warp reads more than once: keep it in L1 ahead of everything else
+__device__ __forceinline__ float2 ldg_keep(const float2 *p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+// ... and the power plane is never read back: do not let it displace X^
+__device__ __forceinline__ void st_stream(float *p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ constexpr int below_pow2_16(int m) {
   return m < 8 ? below_pow2(m) : 8;
 }
@@ -315,7 +326,7 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
             const float2 z = fma2(a64, bc((float)m), zl2);
             const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);
             const float2 d = make_float2(ex2(e.x), ex2(e.y));
-            const float2 v0 = __ldg(xh + 64 * m), v1 = __ldg(xh + 64 * m + 32);
+            const float2 v0 = ldg_keep(xh + 64 * m), v1 = ldg_keep(xh + 64 * m + 32);
             float2 vr = mul2(make_float2(v0.x, v1.x), d), vi = mul2(make_float2(v0.y, v1.y), d);
             if (q) {
               const float4 t = sm.tw_c[q - 1][m][lane];
@@ -330,7 +341,7 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         }
       } else {
         const float d = ex2(fmaf(zl * zl, -0.72134752044f, rp.lognorm));
-        const float2 v0 = __ldg(xh);
+        const float2 v0 = ldg_keep(xh);
         float ar = v0.x * d, ai = v0.y * d;
         if (q) {
           const float4 t = sm.tw_c[q - 1][0][lane];  // (cos, ., sin, .) of 2*pi*q*lane/N
@@ -382,8 +393,8 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-        if (tl + 32 * D * p < n0) orow[32 * D * p] = pw.x;
-        if (tl + 32 * D * p + 512 * D < n0) orow[32 * D * p + 512 * D] = pw.y;
+        if (tl + 32 * D * p < n0) st_stream(orow + 32 * D * p, pw.x);
+        if (tl + 32 * D * p + 512 * D < n0) st_stream(orow + 32 * D * p + 512 * D, pw.y);
       }
     }
   }

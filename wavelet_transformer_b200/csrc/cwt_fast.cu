@@ -258,7 +258,7 @@ template <int D> struct CtaSmemF {
 // X^ is the only data a warp reads more than once: keep it in L1 ahead of everything else
 __device__ __forceinline__ float2 ldg_keep(const float2 *p) {
   float2 v;
-  asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 }
 // ... and the power plane is never read back: do not let it displace X^

@@ -48,6 +48,37 @@ def test_cfg4_shard_parseval_and_batch_invariance(shim):
 
 
 @pytest.mark.timeout(300)
+def test_cfg1_shape_at_batch_scale(shim):
+    """BASELINE cfg1's shape (1346 monthly samples -> nfft 2048, 85 scales) as a 30 000-series
+    device-resident batch: the two-pass-per-row kernel against the generic kernel on sampled
+    series (a 6-series call is below the fast path's threshold), batch-position invariance
+    through duplicated series, and the oracle."""
+    import torch
+    from wavelet_transformer_b200 import engine
+    dev = torch.device("cuda", 0)
+    B, n0, J = 30_000, 1346, 84
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    x = torch.randn((B, n0), generator=g, device=dev, dtype=torch.float32)
+    x = x + 0.1 * torch.cumsum(x, dim=1)
+    x[20_001] = x[0]                                    # the same series at two batch positions
+    x[B - 1] = x[4242]
+    power = torch.empty((B, J + 1, n0), dtype=torch.float32, device=dev)
+    engine.cwt_power_resident(x, power, DT, 1 / 12, 2 * DT, J)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(power[::499]).all())
+    assert torch.equal(power[0], power[20_001]) and torch.equal(power[4242], power[B - 1])
+    idx = torch.tensor([0, 1, 4242, 14_999, 29_998, B - 1], device=dev)
+    alone = torch.empty((idx.numel(), J + 1, n0), dtype=torch.float32, device=dev)
+    engine.cwt_power_resident(x[idx].contiguous(), alone, DT, 1 / 12, 2 * DT, J)
+    torch.cuda.synchronize()
+    scale = alone.amax(dim=(1, 2), keepdim=True)
+    assert float(((alone - power[idx]).abs() / scale).max()) <= 1e-4
+    ref = np.abs(po.cwt(x[14_999].double().cpu().numpy(), DT, 1 / 12, 2 * DT, J)[0]) ** 2
+    assert np.abs(power[14_999].cpu().numpy() - ref).max() <= 1e-4 * ref.max()
+
+
+@pytest.mark.timeout(300)
 def test_cfg5_histogram_totals_and_partition(shim):
     """cfg5 shape (N=3351 -> 4096, 66 scales): every reliable sample of every realisation is
     binned exactly once, and sharding the realisations does not change the histogram."""

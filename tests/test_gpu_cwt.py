@@ -198,3 +198,29 @@ def test_cwt_fp32_nfft2048_interleaved_passes(shim, n0, dj, J):
     small, _ = shim.cwt_morlet(x[:5], DT, dj, 2 * DT, J, f64=False)
     assert np.array_equal(small, gen[:5])
 
+
+
+def test_cwt_fp32_dispatch_fuzz(shim):
+    """Random transform parameters through every FP32 dispatch target (1024 warp kernel, the
+    2048 two-pass kernel, the 4096 register rows, generic): unusual f0, sampling steps, smallest
+    scales below the Nyquist period and very coarse / fine dj move the daughter's band edges, which
+    is what the pruned transforms key on.  Reference = the FP64 generic kernel (itself oracle-gated)."""
+    rng = np.random.default_rng(2026)
+    cases = []
+    for n0 in (1024, 700, 1346, 2048, 1500, 3351, 4096, 300):
+        for _ in range(3):
+            dt = float(rng.choice([1 / 12, 0.25, 1.0, 3.0]))
+            dj = float(rng.choice([1 / 2, 1 / 4, 1 / 7, 1 / 12, 1 / 16]))
+            s0 = dt * float(rng.choice([0.5, 1.0, 2.0, 5.0]))
+            f0 = float(rng.choice([4.0, 6.0, 6.0, 8.5, 12.0]))
+            jmax = int(np.floor(np.log2(n0 * dt / s0) / dj))
+            J = int(rng.integers(max(1, jmax // 2), min(jmax, 120) + 1))
+            cases.append((n0, dt, dj, s0, f0, J))
+    for n0, dt, dj, s0, f0, J in cases:
+        batch = 140 if n0 > 1024 and n0 <= 2048 else 5      # the 2048 kernel starts at 128 series
+        x = rng.standard_normal((batch, n0)) + 0.02 * rng.standard_normal((batch, n0)).cumsum(axis=1)
+        got, _ = shim.cwt_morlet(x, dt, dj, s0, J, f0, f64=False)
+        ref, _ = shim.cwt_morlet(x[:5], dt, dj, s0, J, f0, f64=True, generic_only=True)
+        for b in range(5):
+            ok, err = normwise_close(got[b], ref[b], 1e-4)
+            assert ok, f"n0={n0} dt={dt} dj={dj:.4f} s0={s0} f0={f0} J={J} series {b}: {err:.3e}"

@@ -184,3 +184,46 @@ def test_mc_cfg5_shape_fast_vs_generic_vs_oracle(shim):
     for h in (fast, gen):
         c = h.cumsum(axis=1) / np.maximum(h.sum(axis=1, keepdims=True), 1)
         assert np.abs(c - cref).max() <= 2e-3
+
+
+@pytest.mark.parametrize("dj,J,taps", [(1 / 12, 97, 14), (1 / 4, 33, 5), (1 / 6, 49, 7), (1 / 10, 82, 12)])
+def test_mc_fast_path_other_scale_resolutions(shim, dj, J, taps):
+    """The register-FFT Monte-Carlo kernels at other dj (surrogates still 2049..4096 samples):
+    the scale boxcar has rect(round(1.2/dj)) taps -- 14 and 5 take the register-ring
+    instantiations, 7 and 12 the shared-memory ring.  Injected surrogates, oracle CDFs."""
+    s0 = 2 * DT
+    N, maxscale = shim.wct_mc_geometry(DT, dj, s0, J)
+    assert 2048 < N <= 4096 and int(round(0.6 / dj * 2)) == taps
+    rng = np.random.default_rng(J)
+    mc = 2
+    sur = np.stack([np.stack([po.rednoise(N, 0.9, 1, rng), po.rednoise(N, 0.7, 1, rng)]) for _ in range(mc)])
+    _, hist_ref = po.wct_significance(0.9, 0.7, DT, dj, s0, J, mc_count=mc, surrogates=sur, return_hist=True)
+    fast = shim.wct_mc_hist(0.9, 0.7, DT, dj, s0, J, mc_count=mc, surrogates=sur, f64=False)
+    gen = shim.wct_mc_hist(0.9, 0.7, DT, dj, s0, J, mc_count=mc, surrogates=sur, f64=False, generic_only=True)
+    assert fast.sum() == gen.sum() == hist_ref.sum()
+    cref = hist_ref.cumsum(axis=1) / np.maximum(hist_ref.sum(axis=1, keepdims=True), 1)
+    for h in (fast, gen):
+        c = h.cumsum(axis=1) / np.maximum(h.sum(axis=1, keepdims=True), 1)
+        assert np.abs(c - cref).max() <= 2e-3
+
+
+def test_wct_fp32_fast_path_fuzz(shim):
+    """Random parameters through the nfft = 4096 coherence kernels (other f0, sampling steps, dj,
+    smallest scales): the pruned bands of the daughters and of the Gaussian time filter move with
+    them.  Reference = the FP64 generic kernels (oracle-gated above)."""
+    rng = np.random.default_rng(4096)
+    for _ in range(6):
+        n0 = int(rng.integers(2049, 4097))
+        dt = float(rng.choice([1 / 12, 0.5, 2.0]))
+        dj = float(rng.choice([1 / 4, 1 / 8, 1 / 10, 1 / 12]))
+        s0 = dt * float(rng.choice([1.0, 2.0, 4.0]))
+        f0 = float(rng.choice([6.0, 6.0, 7.5, 10.0]))
+        jmax = int(np.floor(np.log2(n0 * dt / s0) / dj))
+        J = int(rng.integers(jmax // 2, min(jmax, 110) + 1))
+        y1 = _norm(po.rednoise(n0, 0.8, 1, rng))
+        y2 = _norm(0.5 * y1 + po.rednoise(n0, 0.5, 1, rng))
+        wct, phase, w12 = shim.xwt_wct(y1, y2, dt, dj, s0, J, f0, f64=False, want_w12=True)
+        ref, _, ref12 = shim.xwt_wct(y1, y2, dt, dj, s0, J, f0, f64=True, want_w12=True, generic_only=True)
+        tag = f"n0={n0} dt={dt} dj={dj:.4f} s0={s0} f0={f0} J={J}"
+        assert np.abs(w12 - ref12).max() <= 1e-4 * np.abs(ref12).max(), tag
+        assert np.abs(wct - ref).max() <= 5e-3 and np.abs(wct - ref).mean() <= 1e-4, tag

@@ -38,6 +38,9 @@ constexpr int kN = 1024;
 constexpr int kWarpsDefault = 16;     // warps per CTA, one CTA per SM (WTB_CWT_WARPS overrides: 12, 14, 15)
 constexpr int kTrStride = 34;         // floats per row of the transpose buffer (even, == 2 mod 32)
 constexpr float kZCut = 5.3f;         // daughter dropped where |s*w - f0| > kZCut  (exp(-14) ~ 8e-7)
+// pycwt's Morlet has no Heaviside step: at negative frequencies the daughter is exp(-(f0 + |s*w|)^2 / 2)
+// of its peak.  The one-sided transforms here drop that tail, which is below the same 8e-7 only
+// for f0 >= kZCut (f0 = 6, the reference's only value: 1.5e-8); smaller f0 take the generic kernel.
 constexpr int kMaxRows = 256;         // scale rows staged in shared memory
 
 struct RowParam {
@@ -405,7 +408,7 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                  int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (nfft != kN || (flags & WTB_COI_MASK) || f0 < 1.0 || S > kMaxRows) return 1;
+  if (nfft != kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRows) return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
@@ -458,7 +461,7 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   // One warp walks all rows of a series: for a handful of series the generic kernel, which
   // spreads the scales of one series over CTAs, has the shorter critical path (measured
   // crossover below 128 series).
-  if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < 1.0 || S > kMaxRowsF || batch < kMinBatchF) return 1;
+  if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRowsF || batch < kMinBatchF) return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;

@@ -35,6 +35,8 @@ constexpr int kN = 4096;
 constexpr int kThreads = 256;
 constexpr int kBuf = kN + kN / 16;     // padded: index i lives at pad(i) = i + (i >> 4)
 constexpr int kMaxRowsC = 512;         // scale rows the boxcar kernel stages in shared memory
+constexpr double kMinF0 = 5.3;         // one-sided daughters: the dropped negative-frequency tail is
+                                       // exp(-f0^2/2) of the peak (8e-7 at 5.3, 1.5e-8 at the reference's f0 = 6)
 
 struct WRow {
   float a;        // (s/dt) * 2*pi/N : s*w_k = a*k
@@ -514,7 +516,7 @@ static void fill_rows(const Axes &ax, double dt, double f0, std::vector<WRow> *r
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, float2 *d_coef, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (N != kN || f0 < 1.0 || (flags & WTB_COI_MASK) || S > kMaxRowsC) return 1;
+  if (N != kN || f0 < kMinF0 || (flags & WTB_COI_MASK) || S > kMaxRowsC) return 1;
   std::vector<WRow> rows;
   fill_rows(ax, dt, f0, &rows);
   const float2 *tw2 = nullptr, *tw3 = nullptr;
@@ -545,7 +547,7 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
                  float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
                  const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (N != kN || f0 < 1.0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32 || S > kMaxRowsC) return 1;
+  if (N != kN || f0 < kMinF0 || sizeof(WRow) * S > rows_scratch_bytes || win.K > 32 || S > kMaxRowsC) return 1;
   const bool smooth = d_wct || d_hist;
   std::vector<WRow> rows;
   fill_rows(ax, dt, f0, &rows);

@@ -262,3 +262,46 @@ def test_modwt_single_step_helpers(shim, series):
     wfull = mo.modwt(x, "sym4", 4)
     for r in (0, 3, 4):
         assert np.abs(modwt.circular_convolve_mra(filt[r], wfull[r]) - mo.modwtmra(wfull, "sym4")[r]).max() <= 1e-12
+
+
+def test_filterbank_fuzz_blocked_vs_generic_vs_oracle(shim):
+    """Random lengths, level counts, filters and batch sizes through every filterbank entry
+    point, both precisions: the register-blocked kernels (chains, halos, TMA at any alignment,
+    long-row MRA chains) against the one-output-per-thread generic kernels on every case and
+    against the oracle in FP64."""
+    rng = np.random.default_rng(909)
+    names = ["haar", "db2", "db3", "db4", "sym4", "db5"]
+    for case in range(48):
+        name = names[int(rng.integers(len(names)))]
+        lo, hi, rlo, rhi = _bank(name)
+        n = int(rng.choice([rng.integers(8, 64), rng.integers(64, 700), rng.integers(700, 2100), rng.integers(2100, 5000)]))
+        J = int(rng.integers(1, 12))
+        batch = int(rng.choice([1, 2, 7, 33]))
+        f64 = bool(rng.integers(2))
+        tol = 1e-11 if f64 else 3e-5
+        x = rng.standard_normal((batch, n))
+        tag = f"case {case}: {name} n={n} J={J} batch={batch} f64={f64}"
+        w = shim.modwt(x, lo, hi, J, f64=f64)
+        wg = shim.modwt(x, lo, hi, J, f64=f64, generic_only=True)
+        assert np.abs(w - wg).max() <= tol, tag
+        rec = shim.imodwt(w, lo, hi, f64=f64)
+        assert np.abs(rec - shim.imodwt(w, lo, hi, f64=f64, generic_only=True)).max() <= tol, tag
+        assert np.abs(rec - x).max() <= (1e-9 if f64 else 2e-4), tag
+        mra = shim.modwtmra_taps(w, lo, hi, f64=f64)
+        assert np.abs(mra - shim.modwtmra_taps(w, lo, hi, f64=f64, generic_only=True)).max() <= 10 * tol, tag
+        assert np.abs(mra.sum(axis=1) - x).max() <= (1e-9 if f64 else 2e-4), tag
+        if f64:
+            assert np.abs(w[0] - mo.modwt(x[0], name, J)).max() <= 1e-11, tag
+            assert np.abs(mra[0] - mo.modwtmra(np.asarray(w[0]), name)).max() <= 1e-10, tag
+        level = int(rng.integers(0, pw.dwt_max_level(n, lo.size) + 1))
+        packed, lens = shim.wavedec(x, lo, hi, level, f64=f64)
+        packed_g, _ = shim.wavedec(x, lo, hi, level, f64=f64, generic_only=True)
+        assert np.abs(packed - packed_g).max() <= tol, tag + f" level={level}"
+        if f64:
+            ref = np.concatenate(pw.wavedec(x[0], name, level=level))
+            assert np.abs(np.atleast_2d(packed)[0] - ref).max() <= 1e-11, tag + f" level={level}"
+        if level > 0:
+            back = shim.waverec(packed, lens, rlo, rhi, f64=f64)
+            back_g = shim.waverec(packed, lens, rlo, rhi, f64=f64, generic_only=True)
+            assert back.shape == back_g.shape and np.abs(back - back_g).max() <= tol, tag + f" level={level}"
+            assert np.abs(np.atleast_2d(back)[:, :n] - x).max() <= (1e-9 if f64 else 2e-4) or n % 2, tag

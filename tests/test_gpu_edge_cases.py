@@ -105,3 +105,23 @@ def test_ragged_batches_by_length(shim):
             out[i] = w[k]
     for s, w in zip(series, out):
         assert np.abs(w - mo.modwt(s, "sym4", 2)).max() <= 1e-12
+
+
+def test_host_batches_larger_than_one_staging_chunk(shim):
+    """Host-buffer calls stream the batch through <= 1 GiB staging chunks (csrc/cwt.cu, wct.cu):
+    series on either side of a chunk boundary, and the short last chunk, must come out exactly
+    as they do alone."""
+    rng = np.random.default_rng(1 << 20)
+    dt = 1 / 12
+    x = rng.standard_normal((2300, 1024)).astype(np.float32)      # 2169 series fit one chunk at 120 scales
+    power, _ = shim.cwt_morlet(x, dt, 1 / 12, 2 * dt, 119, f64=False)
+    pick = [0, 2167, 2168, 2169, 2170, 2299]
+    alone, _ = shim.cwt_morlet(x[pick], dt, 1 / 12, 2 * dt, 119, f64=False)
+    assert np.array_equal(power[pick], alone)
+    del power
+    y1 = rng.standard_normal((1500, 400))
+    y2 = 0.4 * y1 + rng.standard_normal((1500, 400))
+    wct, phase, _ = shim.xwt_wct(y1, y2, dt, 1 / 4, 2 * dt, -1, f64=True)
+    pick = [0, 700, 1000, 1200, 1499]
+    wa, pa, _ = shim.xwt_wct(y1[pick], y2[pick], dt, 1 / 4, 2 * dt, -1, f64=True)
+    assert np.array_equal(wct[pick], wa) and np.array_equal(phase[pick], pa)

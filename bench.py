@@ -74,6 +74,16 @@ class ClockSampler:
         except OSError:
             pass
 
+    def wait_ready(self, timeout_s: float = 5.0):
+        """Block until the first sample is on disk: nvidia-smi's start-up (NVML init over every
+        GPU of the box, 0.1-1 s) holds driver locks that stall kernel launches of a launch-heavy
+        step for tens of ms -- keep that out of the timed region."""
+        if self.proc is None:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout_s and os.path.getsize(self.file.name) == 0:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -291,17 +301,25 @@ def run_gpu(args):
         metric, unit = "wct_mc_surrogates_per_sec", "surrogates/s"
         alg_bytes = 0.0
         alg_flops = R * 150e6                         # ~150 MFLOP per realisation
+    if sampler:
+        sampler.wait_ready()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = _shim.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps - 1)]   # per-step spread, no syncs
     ev0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step()
+        if i < args.steps - 1:
+            marks[i].record()
     ev1.record()
     torch.cuda.synchronize()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
+    edges = [ev0] + marks + [ev1]
+    per_step = sorted(a.elapsed_time(b) for a, b in zip(edges[:-1], edges[1:]))
+    step_spread = {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]}
     launches = _shim.kernel_launches() - launches0
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -445,6 +463,7 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "ms_per_step_spread": step_spread,
     }
     if secondary:
         line["secondary"] = secondary

@@ -365,14 +365,14 @@ k_wct_boxcar_4096_t(float4 *__restrict__ spec, int S, const WRow *__restrict__ r
           if (i >= 0 && i < S) {
             const int first = i + up - (K - 1);
             if (akk <= s_kc[first < 0 ? 0 : first]) {
-              float4 acc = zero;
+              float2 lo = make_float2(0.0f, 0.0f), hi = lo;  // two FFMA2 per tap, same sums in the same order
 #pragma unroll
               for (int k = 0; k < K; ++k) {                  // k = 0 <-> row s_in, then older rows
                 const float4 g = ring[(slot - k + K) % K];
-                acc.x = fmaf(wk[k], g.x, acc.x); acc.y = fmaf(wk[k], g.y, acc.y);
-                acc.z = fmaf(wk[k], g.z, acc.z); acc.w = fmaf(wk[k], g.w, acc.w);
+                lo = fma2(bc(wk[k]), make_float2(g.x, g.y), lo);
+                hi = fma2(bc(wk[k]), make_float2(g.z, g.w), hi);
               }
-              col[(int64_t)i * kN] = acc;
+              col[(int64_t)i * kN] = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
           }
         }
@@ -431,7 +431,8 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
     for (int r = 0; r < 16; ++r) {
       const int t = j + 256 * r;
       if (t >= lo && t <= hi) {
-        const float r2 = fmaf(R[r].y, R[r].y, I[r].y * I[r].y) / (R[r].x * I[r].x);
+        // binning to 1/1000: the 2-ulp reciprocal-multiply is far inside the bin width
+        const float r2 = __fdividef(fmaf(R[r].y, R[r].y, I[r].y * I[r].y), R[r].x * I[r].x);
         if (r2 >= 0.0f) {   // NaN (0/0) is skipped
           int bin = (int)floorf(r2 * (float)WTB_NBINS);
           bin = min(bin, WTB_NBINS - 1);

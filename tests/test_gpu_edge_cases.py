@@ -125,3 +125,30 @@ def test_host_batches_larger_than_one_staging_chunk(shim):
     pick = [0, 700, 1000, 1200, 1499]
     wa, pa, _ = shim.xwt_wct(y1[pick], y2[pick], dt, 1 / 4, 2 * dt, -1, f64=True)
     assert np.array_equal(wct[pick], wa) and np.array_equal(phase[pick], pa)
+
+
+def test_shutdown_releases_and_next_call_rebuilds(shim):
+    """wtb_shutdown frees every per-thread arena, the parameter buffers and the twiddle tables;
+    the next call must rebuild them and give the same numbers (a stale device pointer would not)."""
+    rng = np.random.default_rng(3)
+    dt = 1 / 12
+    x2 = rng.standard_normal((130, 1346))                     # 2048 two-pass kernel (parameter buffer)
+    x4 = rng.standard_normal((2, 3000))                       # 4096 register rows (radix-16 tables)
+
+    def run():
+        a, _ = shim.cwt_morlet(x2, dt, 1 / 12, 2 * dt, 84, f64=False)
+        b, _ = shim.cwt_morlet(x4, dt, 1 / 8, 2 * dt, 60, f64=False)
+        c = shim.wct_mc_hist(0.9, 0.8, dt, 1 / 8, 2 * dt, 65, mc_count=4, seed=9, f64=False)
+        d = shim.modwt(x4, *[np.array(v) for v in (_la8().dec_lo, _la8().dec_hi)], 5, f64=True)
+        return a, b, c, d
+
+    first = run()
+    shim.shutdown()
+    second = run()
+    for u, v in zip(first, second):
+        assert np.array_equal(u, v)
+
+
+def _la8():
+    from wavelet_transformer_b200 import pywt_compat as pywt
+    return pywt.Wavelet("sym4")

@@ -18,6 +18,7 @@ LIB = PKG / "lib" / "libwavelet_sm100a.so"
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xlinker", "--no-undefined",      # a symbol missing between translation units fails the build, not the first load
 ]
 
 

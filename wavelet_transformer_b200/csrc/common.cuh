@@ -82,6 +82,9 @@ struct Arena {
 int arena_reserve(size_t bytes, void **out);  // thread-local arena, 256B aligned
 // Second independent arena (I/O staging for host-pointer calls).
 int staging_reserve(size_t bytes, void **out);
+// small per-thread buffer for kernel parameter tables, separate from the two arenas above so a
+// callee can fill it while its caller's arena holds live data; released by wtb_shutdown as well
+int params_reserve(size_t bytes, void **out);
 
 // Twiddle table exp(-2*pi*i*k/N), k in [0,N), in precision T; cached per (device,N).
 template <typename T> int twiddles(int N, const cplx<T> **out);

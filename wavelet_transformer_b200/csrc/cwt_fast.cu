@@ -473,9 +473,10 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
     r.multi = khi >= 32;
     r.L = r.multi ? std::max(1, std::min(5, ilog2(khi / 32 + 1))) : ilog2(khi + 1);
   }
-  // the caller's arena holds xhat: row parameters get a small cached buffer of their own
-  static thread_local RowParam *d_rows = nullptr;
-  if (!d_rows) WTB_CUDA(cudaMalloc(&d_rows, sizeof(RowParam) * kMaxRowsF));
+  // the caller's arena holds xhat: row parameters go to the per-thread parameter buffer
+  void *prm = nullptr;
+  WTB_TRY(params_reserve(sizeof(RowParam) * kMaxRowsF, &prm));
+  RowParam *d_rows = (RowParam *)prm;
   // rows.data() is pageable: the copy is staged before the call returns
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
   const int grid = (int)std::min<int64_t>(batch, (int64_t)sm_count());

@@ -108,6 +108,10 @@ int staging_reserve(size_t bytes, void **out) {
   static thread_local Arena *a = new_arena();
   return reserve(a, bytes, out);
 }
+int params_reserve(size_t bytes, void **out) {
+  static thread_local Arena *a = new_arena();
+  return reserve(a, bytes, out);
+}
 
 // ---- twiddles ----------------------------------------------------------------------
 template <typename T> struct TwCache {
@@ -142,6 +146,8 @@ template <typename T> int twiddles(int N, const cplx<T> **out) {
 }
 template int twiddles<float>(int, const cplx<float> **);
 template int twiddles<double>(int, const cplx<double> **);
+
+void wct_fast_release();  // wct_fast.cu: the radix-16 twiddle tables
 
 static void free_tables() {
   {
@@ -221,6 +227,7 @@ void wtb_shutdown(void) {
     }
   }
   free_tables();
+  wct_fast_release();
 }
 
 const char *wtb_last_error(void) { return g_err; }

@@ -479,7 +479,7 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
     WTB_CUDA(cudaMalloc(&d3, sizeof(float2) * 4096));
     WTB_CUDA(cudaMemcpy(d2, h2.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
     WTB_CUDA(cudaMemcpy(d3, h3.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice));
-    g_tab.tw2 = d2;   // kept for the life of the process (34 KB)
+    g_tab.tw2 = d2;   // kept until wtb_shutdown (34 KB)
     g_tab.tw3 = d3;
     g_tab.device = dev;
   }
@@ -489,6 +489,14 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
 }
 
 }  // namespace
+
+// wtb_shutdown: the radix-16 twiddle tables go with the arenas
+void wct_fast_release() {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  if (g_tab.tw2) cudaFree(g_tab.tw2);
+  if (g_tab.tw3) cudaFree(g_tab.tw3);
+  g_tab = Tables();
+}
 
 static void fill_rows(const Axes &ax, double dt, double f0, std::vector<WRow> *rows) {
   const int S = ax.J + 1;
@@ -522,14 +530,10 @@ int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double
   fill_rows(ax, dt, f0, &rows);
   const float2 *tw2 = nullptr, *tw3 = nullptr;
   WTB_TRY(ensure_tables(&tw2, &tw3));
-  // row parameters go to a small cached device buffer of their own (the caller's arena holds xhat)
-  static thread_local WRow *d_rows = nullptr;
-  static thread_local int d_rows_cap = 0;
-  if (d_rows_cap < S) {
-    if (d_rows) WTB_CUDA(cudaFree(d_rows));
-    WTB_CUDA(cudaMalloc(&d_rows, sizeof(WRow) * kMaxRowsC));
-    d_rows_cap = kMaxRowsC;
-  }
+  // row parameters go to the per-thread parameter buffer (the caller's arena holds xhat)
+  void *prm = nullptr;
+  WTB_TRY(params_reserve(sizeof(WRow) * kMaxRowsC, &prm));
+  WRow *d_rows = (WRow *)prm;
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WRow) * S, cudaMemcpyHostToDevice, st));
   const int64_t nrows = (batch + 1) / 2 * S;
   WTB_REQUIRE(nrows < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");

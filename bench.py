@@ -455,8 +455,9 @@ def run_gpu(args):
                     "frac": ach / (fp32_peak_nominal / 1e12), "traffic": args.traffic_bytes,
                     "peak_source": "nominal non-tensor FP32 peak (148 SM x 128 x 2 x 1.965 GHz); this path is "
                                    "FP32-FLOP bound, tensor cores are not applicable (no dense contraction)",
-                    "kernel": "k_wct_spec_4096 (CWT + cross spectrum + Gaussian time filter per scale row; 47% of "
-                              "the step, with k_wct_coh_4096 27% and k_wct_boxcar_4096 8%)",
+                    "kernel": "k_wct_spec_4096 (CWT + cross spectrum + Gaussian time filter per scale row; 56% of "
+                              "the step, with k_wct_coh_4096 30% and k_wct_boxcar_4096 9%: "
+                              "profiles/r1_launches_mc_final.csv)",
                     "algorithmic_flop_per_launch": alg_flops}
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,

@@ -272,11 +272,23 @@ def test_transform_helpers_batch_measures(series):
         assert np.abs(got.significance_levels - one.significance_levels).max() <= 1e-9 * one.significance_levels.max()
         assert np.array_equal(got.period, one.period) and np.array_equal(got.coi, one.coi)
     assert th.create_cwt_results_dict(cdict, ["infl"], calculate_significance=False)["infl"].significance_levels is None
-    # XWT: the per-comparison loop
-    xdict = th.create_xwt_dict(frame, [("infl", "expn")])
-    xres = th.create_xwt_results_dict(xdict, [("infl", "expn")])
-    one = xwt.run_xwt(xdict[("infl", "expn")])
-    assert np.array_equal(xres[("infl", "expn")].power, one.power)
+    # XWT: comparisons of one shape share two launches (cross spectra, phase); a lone one loops
+    frame["expn_lag"] = np.roll(cols["expn"], 7)
+    pairs = [("infl", "expn"), ("expn", "infl"), ("infl", "expn_lag")]
+    xdict = th.create_xwt_dict(frame, pairs)
+    xres = th.create_xwt_results_dict(xdict, pairs)
+    assert list(xres) == pairs
+    for c in pairs:
+        one = xwt.run_xwt(xdict[c])
+        got = xres[c]
+        assert got.power.shape == one.power.shape and got.phase_diff_u.shape == one.phase_diff_u.shape
+        assert np.abs(got.power - one.power).max() <= 1e-12 * np.abs(one.power).max()
+        assert np.allclose(got.significance_levels, one.significance_levels, rtol=1e-10, atol=0)
+        assert np.array_equal(got.period, one.period) and np.allclose(got.coi, one.coi, rtol=1e-13)
+        assert np.abs(got.phase_diff_u - one.phase_diff_u).max() <= 1e-9
+        assert np.abs(got.phase_diff_v - one.phase_diff_v).max() <= 1e-9
+    lone = th.create_xwt_results_dict(xdict, pairs[:1])
+    assert np.array_equal(lone[pairs[0]].power, xwt.run_xwt(xdict[pairs[0]]).power)
 
 
 def test_entry_points_are_reentrant_across_host_threads(shim, series):

@@ -134,5 +134,20 @@ def create_cwt_results_dict(cwt_data_dict: Dict[str, DataForCWT], measures_list:
 
 def create_xwt_results_dict(xwt_data_dict: Dict[Tuple[str, str], DataForXWT], xwt_list: List[Tuple[str, str]],
                             **kwargs) -> Dict[Tuple[str, str], ResultsFromXWT]:
-    """``run_xwt`` of every comparison (transform_helpers.py:127-140)."""
-    return {comparison: xwt.run_xwt(xwt_data_dict[comparison], **kwargs) for comparison in xwt_list}
+    """``run_xwt`` of every comparison (transform_helpers.py:127-140); comparisons of one shape
+    share the two launches of ``run_xwt_batch``."""
+    def shape_of(c):
+        d = xwt_data_dict[c]
+        mother = wavelet._as_mother(d.mother_wavelet)
+        if not isinstance(mother, wavelet.Morlet) or len(d.y1_values) != len(d.y2_values):
+            return ("single", c)
+        return (len(d.y1_values), d.delta_t, d.delta_j, d.initial_scale, mother.f0)
+
+    out = {}
+    for shape, members in _groups(list(dict.fromkeys(xwt_list)), shape_of).items():
+        if shape[0] == "single" or len(members) == 1:
+            for c in members:
+                out[c] = xwt.run_xwt(xwt_data_dict[c], **kwargs)
+        else:
+            out.update(zip(members, xwt.run_xwt_batch([xwt_data_dict[c] for c in members], **kwargs)))
+    return {c: out[c] for c in xwt_list}

@@ -81,3 +81,51 @@ def run_xwt(cross_wavelet_transform: Type[DataForXWT], normalize: bool = True) -
                                     normalize=True, cache=True)
     u, v = calculate_phase_difference(phase)
     return ResultsFromXWT(power, period, ratio, coi_plot, u, v)
+
+
+def run_xwt_batch(items: List[Type[DataForXWT]], normalize: bool = True) -> List[Type[ResultsFromXWT]]:
+    """``run_xwt`` of several comparisons that share one shape (series length, dt, dj, s0, Morlet
+    f0) as two batched launches -- the cross spectra, then the phase at the default dj = 1/12 the
+    reference's second call ends up with -- instead of two per comparison
+    (src/utils/transform_helpers.py:127-140 loops ``run_xwt``).  Entry by entry the result equals
+    ``run_xwt``'s; ``ar1`` still raises ``Warning`` for a series it cannot bound."""
+    if not items:
+        return []
+    from .. import _shim
+    d0 = items[0]
+    mother = wavelet._as_morlet(d0.mother_wavelet)
+    n = d0.y1_values.size
+    for d in items:
+        same = (d.y1_values.size == n and d.y2_values.size == n and d.delta_t == d0.delta_t
+                and d.delta_j == d0.delta_j and d.initial_scale == d0.initial_scale
+                and wavelet._as_morlet(d.mother_wavelet).f0 == mother.f0)
+        if not same:
+            raise ValueError("run_xwt_batch takes comparisons of one shape")
+    dt, dj, s0 = d0.delta_t, d0.delta_j, d0.initial_scale
+    y1 = np.stack([np.asarray(d.y1_values, dtype=float) for d in items])
+    y2 = np.stack([np.asarray(d.y2_values, dtype=float) for d in items])
+    a = (y1 - y1.mean(axis=1, keepdims=True)) / y1.std(axis=1, keepdims=True)     # pycwt.xwt(normalize=True)
+    b = (y2 - y2.mean(axis=1, keepdims=True)) / y2.std(axis=1, keepdims=True)
+    Jr, _, freqs, coi = wavelet._resolve_s0_J(n, dt, dj, s0, -1, mother)
+    _, _, w12 = _shim.xwt_wct(a, b, dt, dj, s0, Jr, mother.f0, want_wct=False, want_phase=False, want_w12=True)
+    w12 = np.asarray(w12, dtype=np.complex128).reshape(len(items), Jr + 1, n)
+    # the phase call: pycwt.wct(..., delta_j=dj) swallows the keyword, so dj = 1/12 and J follows from it
+    dj_phase = 1 / 12
+    J_phase = int(np.round(np.log2(n * dt / s0) / dj_phase))
+    _, phase, _ = _shim.xwt_wct(a, b, dt, dj_phase, s0, J_phase, mother.f0, want_wct=False, want_phase=True)
+    phase = np.asarray(phase, dtype=float).reshape(len(items), J_phase + 1, n)
+    dof = mother.dofmin
+    out = []
+    for i, d in enumerate(items):
+        a1, a2 = wavelet.ar1(y1[i])[0], wavelet.ar1(y2[i])[0]
+        pk = (wavelet.ar1_spectrum(freqs * dt, a1) * wavelet.ar1_spectrum(freqs * dt, a2)) ** 0.5
+        signif = pk * wavelet._chi2_ppf(0.95, dof) / dof       # std1 = std2 = 1 after normalisation
+        if normalize:
+            period, power, ratio, coi_plot = wavelet_helpers.normalize_xwt_results(
+                n, w12[i], coi, np.log2(d.levels[2]), freqs, signif)
+        else:
+            period, power, coi_plot = 1 / freqs, w12[i], coi
+            ratio = power / (np.ones([1, n]) * signif[:, None])
+        u, v = calculate_phase_difference(phase[i])
+        out.append(ResultsFromXWT(power, period, ratio, coi_plot, u, v))
+    return out

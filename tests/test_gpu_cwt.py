@@ -224,3 +224,28 @@ def test_cwt_fp32_dispatch_fuzz(shim):
         for b in range(5):
             ok, err = normwise_close(got[b], ref[b], 1e-4)
             assert ok, f"n0={n0} dt={dt} dj={dj:.4f} s0={s0} f0={f0} J={J} series {b}: {err:.3e}"
+
+
+@pytest.mark.parametrize("n0,batch", [(512, 6), (400, 7), (257, 1), (300, 33)])
+def test_cwt_fp32_nfft512_two_series_per_warp(shim, n0, batch):
+    """Series of 257..512 samples share the 1024-point warp kernel two at a time (even / odd bins
+    of the interleaved spectrum, sum / difference of the two output halves); an odd batch leaves
+    the last warp with one series.  Oracle and generic-kernel parity, and pairing must not leak:
+    a series gives the same plane whatever its partner is."""
+    rng = np.random.default_rng(n0 + batch)
+    x = rng.standard_normal((batch, n0)) * rng.uniform(0.1, 30.0, size=(batch, 1))   # very different amplitudes
+    dj, J = 1 / 12, int(np.floor(np.log2(n0 * DT / (2 * DT)) * 12))
+    power, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False)
+    gen, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, generic_only=True)
+    assert power.shape == (batch, J + 1, n0)
+    for b in range(batch):
+        ok, err = normwise_close(power[b], gen[b], 1e-4)
+        assert ok, f"series {b}: {err:.3e} vs the generic kernel"
+    for b in sorted({0, batch - 1}):
+        ref = np.abs(_oracle_plane(x[b], DT, dj, 2 * DT, J)) ** 2
+        ok, err = normwise_close(power[b], ref, 1e-4)
+        assert ok, f"series {b}: {err:.3e} vs the oracle"
+    if batch >= 3:
+        swapped, _ = shim.cwt_morlet(x[[0, 2, 1]], DT, dj, 2 * DT, J, f64=False)
+        ok, err = normwise_close(swapped[0], power[0], 2e-6)
+        assert ok, f"series 0 changed with its partner: {err:.3e}"

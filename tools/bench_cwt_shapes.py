@@ -35,7 +35,7 @@ def main():
     dt = 1 / 12
     shapes = [("cfg1 shape", 1346, 1 / 12, 84, 20000), ("nfft 2048 full", 2048, 1 / 12, 84, 20000),
               ("odd rows", 1345, 1 / 12, 84, 20000), ("cfg4", 1024, 1 / 12, 119, 20000),
-              ("nfft 4096", 3351, 1 / 8, 65, 4000)]
+              ("nfft 4096", 3351, 1 / 8, 65, 4000), ("nfft 512", 400, 1 / 12, 91, 40000)]
     for label, n0, dj, J, batch in shapes:
         if args.only and args.only not in label:
             continue

@@ -84,7 +84,15 @@ __device__ __forceinline__ constexpr int below_pow2(int m) {
 
 // One dit32 call site serves the forward transform (s = -1), step A and step B of
 // every scale row: the hot code stays inside the instruction cache.
-template <int kWarps>
+//
+// HALF = true serves nfft = 512 (series of 257..512 samples) with the same 1024-point machinery,
+// TWO SERIES per warp: series A takes the even bins of the 1024-point spectrum, series B the odd
+// ones, Z[2k] = Y_A[k], Z[2k+1] = Y_B[k].  Then x[t] = a[t] + w1024^t b[t] and
+// x[t+512] = a[t] - w1024^t b[t] with a, b the two 512-point inverse transforms, and t, t+512 are
+// the two halves of one packed register: |a|^2 = |x[t] + x[t+512]|^2 / 4, |b|^2 likewise with
+// the difference (the phase w^t drops out of the power).  The forward transforms of both real
+// series come from one pass over A - iB repeated twice (even bins = the 512-point spectrum).
+template <int kWarps, bool HALF>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
                 const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
@@ -109,13 +117,16 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
   const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
   const bool full_row = (n0 == kN);
-  const float lanef = (float)lane;
+  // HALF: bin k = lane + 32 k2 belongs to series (lane & 1) and is its bin (k - (lane & 1)) / 2
+  const float lanef = (float)(HALF ? (lane & ~1) : lane);
   const int tidx = 2 * (lane & 15) + (lane >> 4);   // column of this lane (as t2) in the transpose buffer
   float2 R[16], I[16];
 
-  for (int64_t b = gwarp; b < batch; b += nwarps) {
-    const float *xr = x + b * n0;
-    float *out = power + b * (int64_t)S * n0 + lane;
+  const int64_t items = HALF ? (batch + 1) / 2 : batch;   // HALF: one warp item = series 2b and 2b + 1
+  for (int64_t b = gwarp; b < items; b += nwarps) {
+    const float *xr = x + (HALF ? 2 * b : b) * n0;
+    const bool has_b = !HALF || 2 * b + 1 < batch;
+    float *out = power + (HALF ? 2 * b : b) * (int64_t)S * n0 + lane;
 #pragma unroll 1
     for (int s = -1; s < S; ++s) {
       int L, two_pass;
@@ -124,8 +135,17 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const int k = lane + 64 * m;
-          R[br4(m)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, k + 32 < n0 ? __ldg(xr + k + 32) : 0.0f);
-          I[br4(m)] = make_float2(0.0f, 0.0f);
+          if (HALF) {
+            // conj(z), z[t] = A[t mod 512] + i B[t mod 512]: the periodic repeat puts the 512-point
+            // spectrum of z on the even bins
+            const int t0 = k & 511, t1 = (k + 32) & 511;
+            const float *xb = xr + n0;
+            R[br4(m)] = make_float2(t0 < n0 ? __ldg(xr + t0) : 0.0f, t1 < n0 ? __ldg(xr + t1) : 0.0f);
+            I[br4(m)] = make_float2(has_b && t0 < n0 ? -__ldg(xb + t0) : 0.0f, has_b && t1 < n0 ? -__ldg(xb + t1) : 0.0f);
+          } else {
+            R[br4(m)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, k + 32 < n0 ? __ldg(xr + k + 32) : 0.0f);
+            I[br4(m)] = make_float2(0.0f, 0.0f);
+          }
         }
         L = 5;
         two_pass = 1;
@@ -195,7 +215,37 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
         __syncwarp();
         fft32::dit32(R, I, 5);      // step B is always a full transform: its own straight-line site
       }
-      if (s < 0) {
+      if (s < 0 && HALF) {
+        // FFT1024(z repeated)[2 kk] = 2 Z[kk] = 2 conj(u[2 kk]); even lanes hold kk = lane/2 + 16 t1.
+        // Park Z/2 in the (now free) transpose buffer, then split it into the two real series'
+        // spectra: A^ = (Z[kk] + conj Z[-kk]) / 2, B^ = (Z[kk] - conj Z[-kk]) / 2i, kk < 256.
+        float *zr = ws.trr, *zi = ws.tri;
+        if ((lane & 1) == 0) {
+#pragma unroll
+          for (int t1 = 0; t1 < 16; ++t1) {
+            zr[(lane >> 1) + 16 * t1] = 0.25f * R[t1].x;
+            zi[(lane >> 1) + 16 * t1] = -0.25f * I[t1].x;
+            zr[(lane >> 1) + 16 * (t1 + 16)] = 0.25f * R[t1].y;
+            zi[(lane >> 1) + 16 * (t1 + 16)] = -0.25f * I[t1].y;
+          }
+        }
+        __syncwarp();
+        const bool odd = lane & 1;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          float vr[2], vi[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int kk = (lane >> 1) + 16 * (2 * m + h), j = (512 - kk) & 511;
+            const float ar = zr[kk], ai = zi[kk], br = zr[j], bi = zi[j];   // Z[kk]/2 and Z[-kk]/2 (unconjugated)
+            vr[h] = odd ? ai + bi : ar + br;
+            vi[h] = odd ? br - ar : ai - bi;
+          }
+          ws.xr[m][lane] = make_float2(vr[0], vr[1]);
+          ws.xi[m][lane] = make_float2(vi[0], vi[1]);
+        }
+        __syncwarp();
+      } else if (s < 0) {
         // X^[lane + 32 t1] = conj(u[t1]), t1 < 16 (positive frequencies only)
         float *pr = reinterpret_cast<float *>(&ws.xr[0][0]);
         float *pi = reinterpret_cast<float *>(&ws.xi[0][0]);
@@ -205,6 +255,19 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           pi[(t1 >> 1) * 64 + lane * 2 + (t1 & 1)] = -I[t1].x;
         }
         __syncwarp();
+      } else if (HALF) {
+        // (x[t], x[t+512]) share a register: a = (sum)/2, b = (difference)/2 up to a phase; the 1/2
+        // rides in lognorm (1/1024 instead of 1/512)
+        float *orow = out + (int64_t)s * n0;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const float sr = R[p].x + R[p].y, si = I[p].x + I[p].y;
+          const float dr = R[p].x - R[p].y, di = I[p].x - I[p].y;
+          if (lane + 32 * p < n0) {
+            __stcs(orow + 32 * p, fmaf(sr, sr, si * si));
+            if (has_b) __stcs(orow + (int64_t)S * n0 + 32 * p, fmaf(dr, dr, di * di));
+          }
+        }
       } else {
         float *orow = out + (int64_t)s * n0;
         if (full_row) {
@@ -408,11 +471,15 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                  int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (nfft != kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRows) return 1;
+  // nfft = 512 runs two series per warp on the interleaved 1024-point spectrum (HALF): in that
+  // domain a series' bin kk sits at k = 2 kk + parity, so a, lognorm and the band edge are those
+  // of a 1024-point transform with the edge one bin further out
+  const bool half = nfft == kN / 2;
+  if ((nfft != kN && !half) || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRows) return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
-    int khi = (int)std::floor((f0 + kZCut) / a);
+    int khi = (int)std::floor((f0 + kZCut) / a) + (half ? 1 : 0);
     if (khi > kN / 2 - 1) khi = kN / 2 - 1;
     if (khi < 1) khi = 1;
     RowParam &r = rows[s];
@@ -438,12 +505,21 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
   auto launch = [&](auto tag) -> int {
     constexpr int W = decltype(tag)::value;
     const size_t smem = sizeof(CtaSmem<W>);
-    WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<int64_t>(batch, (int64_t)sm_count());
-    k_cwt_fast_1024<W><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
+    k_cwt_fast_1024<W, false><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   };
+  if (half) {
+    constexpr int W = kWarpsDefault;
+    const size_t smem = sizeof(CtaSmem<W>);
+    WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((batch + 1) / 2, (int64_t)sm_count());
+    k_cwt_fast_1024<W, true><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
+    WTB_LAUNCH_CHECK();
+    return WTB_OK;
+  }
   switch (warps) {
     case 12: return launch(std::integral_constant<int, 12>{});
     case 14: return launch(std::integral_constant<int, 14>{});

@@ -177,7 +177,7 @@ def test_cwt_fp32_nfft4096_register_rows(shim, n0, batch):
 
 
 @pytest.mark.parametrize("n0,dj,J", [(1346, 1 / 12, 84), (1345, 1 / 12, 84), (2048, 1 / 8, 70), (1025, 1 / 4, -1)])
-def test_cwt_fp32_nfft2048_interleaved_passes(shim, n0, dj, J):
+def test_cwt_fp32_nfft2048_interleaved_passes(shim, monkeypatch, n0, dj, J):
     """Batches of 1025..2048-sample series (BASELINE cfg1's 1346-month CPI shape) take the
     warp-autonomous 1024-point kernel twice per row (even / odd output samples), even and odd
     row lengths.  Oracle parity on sampled series, generic-kernel parity on all."""
@@ -194,7 +194,8 @@ def test_cwt_fp32_nfft2048_interleaved_passes(shim, n0, dj, J):
         ref = np.abs(_oracle_plane(x[b], DT, dj, 2 * DT, J)) ** 2
         ok, err = normwise_close(power[b], ref, 1e-4)
         assert ok, f"series {b}: {err:.3e} vs the oracle"
-    # below the threshold the generic kernel serves the call: same numbers either way
+    # below the default threshold the generic kernel serves the call
+    monkeypatch.delenv("WTB_CWT_MIN_BATCH")
     small, _ = shim.cwt_morlet(x[:5], DT, dj, 2 * DT, J, f64=False)
     assert np.array_equal(small, gen[:5])
 
@@ -249,3 +250,21 @@ def test_cwt_fp32_nfft512_two_series_per_warp(shim, n0, batch):
         swapped, _ = shim.cwt_morlet(x[[0, 2, 1]], DT, dj, 2 * DT, J, f64=False)
         ok, err = normwise_close(swapped[0], power[0], 2e-6)
         assert ok, f"series 0 changed with its partner: {err:.3e}"
+
+
+@pytest.mark.parametrize("n0,below,above", [(1024, 95, 96), (565, 40, 100), (400, 319, 320), (1346, 127, 128)])
+def test_cwt_fp32_small_batches_take_the_generic_kernel(shim, monkeypatch, n0, below, above):
+    """One warp walks all rows of a series in the fast kernels (~0.13 ms at any batch) while the
+    generic kernel spreads a series' scales over CTAs (0.02 ms for one series): below the measured
+    break-even the dispatch must pick the generic kernel, at it the fast one."""
+    monkeypatch.delenv("WTB_CWT_MIN_BATCH")
+    rng = np.random.default_rng(n0)
+    x = rng.standard_normal((above, n0))
+    J = 60
+    gen, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, J, f64=False, generic_only=True)
+    lo, _ = shim.cwt_morlet(x[:below], DT, 1 / 8, 2 * DT, J, f64=False)
+    hi, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, J, f64=False)
+    assert np.array_equal(lo, gen[:below])
+    assert not np.array_equal(hi, gen)
+    ok, err = normwise_close(hi[0], gen[0], 1e-4)
+    assert ok, err

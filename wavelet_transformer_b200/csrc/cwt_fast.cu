@@ -468,6 +468,12 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
 
 }  // namespace
 
+// smallest batch the warp-per-series kernels take (WTB_CWT_MIN_BATCH overrides; tests set 1)
+static int64_t min_fast_batch(int64_t dflt) {
+  const char *e = std::getenv("WTB_CWT_MIN_BATCH");
+  return e ? std::atoll(e) : dflt;
+}
+
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                  int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
@@ -476,6 +482,10 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
   // of a 1024-point transform with the edge one bin further out
   const bool half = nfft == kN / 2;
   if ((nfft != kN && !half) || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRows) return 1;
+  // One warp walks every row of its series, ~0.13 ms whatever the batch; the generic kernel spreads
+  // the scales of a series over CTAs and takes 0.02 ms for one series.  Measured crossovers: ~80
+  // series at 1024 x 120 and 565 x 66, ~280 at 400 x 92 (two series per warp).
+  if (batch < min_fast_batch(half ? 320 : 96)) return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
@@ -537,7 +547,8 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   // One warp walks all rows of a series: for a handful of series the generic kernel, which
   // spreads the scales of one series over CTAs, has the shorter critical path (measured
   // crossover below 128 series).
-  if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRowsF || batch < kMinBatchF) return 1;
+  if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF))
+    return 1;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;

@@ -66,8 +66,16 @@ def run_cwt(cwt_data: Type[DataForCWT], normalize: bool = True, standardize: boo
     y = cwt_data.y_values
     signal = standardize_series(y, **kwargs) if standardize else y
     alpha, _, _ = wavelet.ar1(y)
-    wave, scales, freqs, coi, _, _ = wavelet.cwt(signal, DT, DJ, S0, J, cwt_data.mother_wavelet)
-    power = np.abs(wave) ** 2
+    mother = wavelet._as_mother(cwt_data.mother_wavelet)
+    if isinstance(mother, wavelet.Morlet):
+        # |W|^2 straight from the fused kernel: no complex plane over PCIe, no host abs()**2, and
+        # none of the side outputs of pycwt.cwt the reference discards (src/cwt.py:109)
+        _, scales, freqs, coi = wavelet._resolve_s0_J(np.size(signal), DT, DJ, S0, J, mother)
+        power, _ = _shim.cwt_morlet(np.asarray(signal, dtype=float), DT, DJ, S0, int(J), mother.f0)
+        power = np.asarray(power, dtype=float)
+    else:
+        wave, scales, freqs, coi, _, _ = wavelet.cwt(signal, DT, DJ, S0, J, mother)
+        power = np.abs(wave) ** 2
     period = 1 / freqs
     ratio = None
     if calculate_significance:

@@ -234,7 +234,7 @@ def test_cwt_fp32_nfft512_two_series_per_warp(shim, n0, batch):
     the last warp with one series.  Oracle and generic-kernel parity, and pairing must not leak:
     a series gives the same plane whatever its partner is."""
     rng = np.random.default_rng(n0 + batch)
-    x = rng.standard_normal((batch, n0)) * rng.uniform(0.1, 30.0, size=(batch, 1))   # very different amplitudes
+    x = rng.standard_normal((batch, n0)) * 10.0 ** rng.uniform(-4, 5, size=(batch, 1))   # amplitudes over 9 decades
     dj, J = 1 / 12, int(np.floor(np.log2(n0 * DT / (2 * DT)) * 12))
     power, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False)
     gen, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, generic_only=True)
@@ -248,7 +248,7 @@ def test_cwt_fp32_nfft512_two_series_per_warp(shim, n0, batch):
         assert ok, f"series {b}: {err:.3e} vs the oracle"
     if batch >= 3:
         swapped, _ = shim.cwt_morlet(x[[0, 2, 1]], DT, dj, 2 * DT, J, f64=False)
-        ok, err = normwise_close(swapped[0], power[0], 2e-6)
+        ok, err = normwise_close(swapped[0], power[0], 5e-6)
         assert ok, f"series 0 changed with its partner: {err:.3e}"
 
 

@@ -126,6 +126,7 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
   for (int64_t b = gwarp; b < items; b += nwarps) {
     const float *xr = x + (HALF ? 2 * b : b) * n0;
     const bool has_b = !HALF || 2 * b + 1 < batch;
+    float unscale_a = 1.0f, unscale_b = 1.0f;              // HALF: 4^exponent of each series' pre-scaling
     float *out = power + (HALF ? 2 * b : b) * (int64_t)S * n0 + lane;
 #pragma unroll 1
     for (int s = -1; s < S; ++s) {
@@ -145,6 +146,32 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           } else {
             R[br4(m)] = make_float2(k < n0 ? __ldg(xr + k) : 0.0f, k + 32 < n0 ? __ldg(xr + k + 32) : 0.0f);
             I[br4(m)] = make_float2(0.0f, 0.0f);
+          }
+        }
+        if (HALF) {
+          // The two series share one transform, so round-off scales with the LARGER of them: bring
+          // each to [0.5, 1) by an exact power of two first and give the factor back to its power.
+          float ma = 0.0f, mb = 0.0f;
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            ma = fmaxf(ma, fmaxf(fabsf(R[m].x), fabsf(R[m].y)));
+            mb = fmaxf(mb, fmaxf(fabsf(I[m].x), fabsf(I[m].y)));
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+          }
+          int ea = 0, eb = 0;
+          if (ma > 0.0f && ma < INFINITY) frexpf(ma, &ea);
+          if (mb > 0.0f && mb < INFINITY) frexpf(mb, &eb);
+          const float2 sa = bc(ldexpf(1.0f, -ea)), sb = bc(ldexpf(1.0f, -eb));
+          unscale_a = ldexpf(1.0f, 2 * ea);
+          unscale_b = ldexpf(1.0f, 2 * eb);
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            R[m] = mul2(R[m], sa);
+            I[m] = mul2(I[m], sb);
           }
         }
         L = 5;
@@ -264,8 +291,8 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
           const float sr = R[p].x + R[p].y, si = I[p].x + I[p].y;
           const float dr = R[p].x - R[p].y, di = I[p].x - I[p].y;
           if (lane + 32 * p < n0) {
-            __stcs(orow + 32 * p, fmaf(sr, sr, si * si));
-            if (has_b) __stcs(orow + (int64_t)S * n0 + 32 * p, fmaf(dr, dr, di * di));
+            __stcs(orow + 32 * p, fmaf(sr, sr, si * si) * unscale_a);
+            if (has_b) __stcs(orow + (int64_t)S * n0 + 32 * p, fmaf(dr, dr, di * di) * unscale_b);
           }
         }
       } else {

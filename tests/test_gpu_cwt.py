@@ -252,11 +252,12 @@ def test_cwt_fp32_nfft512_two_series_per_warp(shim, n0, batch):
         assert ok, f"series 0 changed with its partner: {err:.3e}"
 
 
-@pytest.mark.parametrize("n0,below,above", [(1024, 95, 96), (565, 40, 100), (400, 319, 320), (1346, 127, 128)])
+@pytest.mark.parametrize("n0,below,above", [(400, 19, 20), (1346, 11, 12)])
 def test_cwt_fp32_small_batches_take_the_generic_kernel(shim, monkeypatch, n0, below, above):
-    """One warp walks all rows of a series in the fast kernels (~0.13 ms at any batch) while the
-    generic kernel spreads a series' scales over CTAs (0.02 ms for one series): below the measured
-    break-even the dispatch must pick the generic kernel, at it the fast one."""
+    """Small batches: the warp kernels split a series' rows over up to 16 warps, which puts the
+    1024 kernel ahead of the generic one from a single series on; the two-series-per-warp (512)
+    and two-pass (2048) variants have measured break-evens of 20 and 12 series, below which the
+    dispatch must pick the generic kernel."""
     monkeypatch.delenv("WTB_CWT_MIN_BATCH")
     rng = np.random.default_rng(n0)
     x = rng.standard_normal((above, n0))
@@ -267,4 +268,23 @@ def test_cwt_fp32_small_batches_take_the_generic_kernel(shim, monkeypatch, n0, b
     assert np.array_equal(lo, gen[:below])
     assert not np.array_equal(hi, gen)
     ok, err = normwise_close(hi[0], gen[0], 1e-4)
+    assert ok, err
+
+
+@pytest.mark.parametrize("n0,S,dj", [(1024, 64, 1 / 8), (565, 66, 1 / 8), (1024, 7, 1), (2048, 30, 1 / 4), (400, 92, 1 / 12)])
+def test_cwt_fp32_row_split_is_invisible(shim, n0, S, dj):
+    """Fewer series than warps on the machine: each series' scale rows are dealt out to up to 16
+    warps (row c, c + split, ...), every one repeating the forward transform.  The split depends
+    on the batch size only, so a series must come out bit-identical at any batch size (2400
+    series: no split), and equal to the oracle."""
+    rng = np.random.default_rng(n0 + S)
+    J = S - 1
+    big = rng.standard_normal((2400, n0))
+    ref_big, _ = shim.cwt_morlet(big, DT, dj, 2 * DT, J, f64=False)
+    # 257..512 samples: two series share a warp, so only whole pairs keep their rounding
+    for batch in ((2, 4, 40, 150, 600) if n0 <= 512 else (1, 3, 40, 149, 600)):
+        power, _ = shim.cwt_morlet(big[:batch], DT, dj, 2 * DT, J, f64=False)
+        assert np.array_equal(power, ref_big[:batch]), f"batch {batch}"
+    ref = np.abs(_oracle_plane(big[2], DT, dj, 2 * DT, J)) ** 2
+    ok, err = normwise_close(ref_big[2], ref, 1e-4)
     assert ok, err

@@ -95,7 +95,7 @@ __device__ __forceinline__ constexpr int below_pow2(int m) {
 template <int kWarps, bool HALF>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
-                const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
+                const RowParam *__restrict__ rows, float f0, float *__restrict__ power, int split) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem<kWarps> &sm = *reinterpret_cast<CtaSmem<kWarps> *>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -122,14 +122,19 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
   const int tidx = 2 * (lane & 15) + (lane >> 4);   // column of this lane (as t2) in the transpose buffer
   float2 R[16], I[16];
 
-  const int64_t items = HALF ? (batch + 1) / 2 : batch;   // HALF: one warp item = series 2b and 2b + 1
-  for (int64_t b = gwarp; b < items; b += nwarps) {
+  // One warp item = one series (HALF: series 2b and 2b + 1) and every split-th scale row from row c
+  // on: a batch too small to give every warp of the machine a series is spread by rows instead
+  // (each item repeats the forward transform, 1 / S of a series' work).  split = 1: all rows.
+  const int64_t items = (HALF ? (batch + 1) / 2 : batch) * split;
+  for (int64_t it = gwarp; it < items; it += nwarps) {
+    const int64_t b = it / split;
+    const int c = (int)(it - b * split);
     const float *xr = x + (HALF ? 2 * b : b) * n0;
     const bool has_b = !HALF || 2 * b + 1 < batch;
     float unscale_a = 1.0f, unscale_b = 1.0f;              // HALF: 4^exponent of each series' pre-scaling
     float *out = power + (HALF ? 2 * b : b) * (int64_t)S * n0 + lane;
 #pragma unroll 1
-    for (int s = -1; s < S; ++s) {
+    for (int s = -1; s < S; s = s < 0 ? c : s + split) {
       int L, two_pass;
       if (s < 0) {
         // forward FFT of the real series: X^[t] = conj(sum_k x[k] w^(+k t))
@@ -333,7 +338,7 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 // wct_fast.cu: its stride-4 stores turn every 32-byte sector into four 8-byte L2 write requests
 // and the L2 request rate becomes the limit.  It was dropped.
 constexpr int kMaxRowsF = 128;
-constexpr int kMinBatchF = 128;
+constexpr int kMinBatchF = 12;
 
 struct WarpSmemF {
   float trr[32 * kTrStride];        // transpose buffer; its first 32 floats double as Y[k] of a single-pass row
@@ -366,7 +371,7 @@ __device__ __forceinline__ constexpr int below_pow2_16(int m) {
 template <int D>
 __global__ void __launch_bounds__(kWarpsDefault * 32, 1)
 k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
-                const RowParam *__restrict__ rows, float f0, float *__restrict__ power) {
+                const RowParam *__restrict__ rows, float f0, float *__restrict__ power, int split) {
   constexpr int kNF = kN * D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmemF<D> &sm = *reinterpret_cast<CtaSmemF<D> *>(smem_raw);
@@ -399,11 +404,14 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
   const int tidx = 2 * (lane & 15) + (lane >> 4);
   float2 R[16], I[16];
 
-  for (int64_t b = gwarp; b < batch; b += nwarps) {
+  // one warp item = one series and every split-th scale row from row c on (see k_cwt_fast_1024)
+  for (int64_t it = gwarp; it < batch * split; it += nwarps) {
+    const int64_t b = it / split;
+    const int c = (int)(it - b * split);
     const float2 *xh = xhat + b * kNF + lane;
     float *out = power + b * (int64_t)S * n0 + D * lane;
 #pragma unroll 1
-    for (int sq = 0; sq < D * S; ++sq) {
+    for (int sq = D * c; sq < D * S; sq = (sq % D == D - 1) ? sq + D * (split - 1) + 1 : sq + 1) {
       const int s = sq / D, q = sq % D;
       const RowParam rp = sm.row[s];
       const int L = rp.L, two_pass = rp.multi;
@@ -509,10 +517,14 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
   // of a 1024-point transform with the edge one bin further out
   const bool half = nfft == kN / 2;
   if ((nfft != kN && !half) || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRows) return 1;
-  // One warp walks every row of its series, ~0.13 ms whatever the batch; the generic kernel spreads
-  // the scales of a series over CTAs and takes 0.02 ms for one series.  Measured crossovers: ~80
-  // series at 1024 x 120 and 565 x 66, ~280 at 400 x 92 (two series per warp).
-  if (batch < min_fast_batch(half ? 320 : 96)) return 1;
+  // With the rows of a series split over warps (below) this kernel is ahead of the generic one at
+  // every batch size for nfft = 1024 (0.017 ms for one series against 0.018); two series per warp
+  // (nfft = 512) pays off from about 20 series (0.021 ms flat against 0.017 + 0.4 us per series).
+  if (batch < min_fast_batch(half ? 20 : 1)) return 1;
+  // fewer series than warps on the machine: split each series' rows over up to 16 warps
+  const int64_t series_items = half ? (batch + 1) / 2 : batch;
+  const int64_t machine_warps = (int64_t)sm_count() * kWarpsDefault;
+  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), machine_warps / series_items));
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / kN;
@@ -543,8 +555,8 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
     constexpr int W = decltype(tag)::value;
     const size_t smem = sizeof(CtaSmem<W>);
     WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<int64_t>(batch, (int64_t)sm_count());
-    k_cwt_fast_1024<W, false><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
+    const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
+    k_cwt_fast_1024<W, false><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power, split);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   };
@@ -552,8 +564,8 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
     constexpr int W = kWarpsDefault;
     const size_t smem = sizeof(CtaSmem<W>);
     WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<int64_t>((batch + 1) / 2, (int64_t)sm_count());
-    k_cwt_fast_1024<W, true><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power);
+    const int grid = (int)std::min<int64_t>(series_items * split, (int64_t)sm_count());
+    k_cwt_fast_1024<W, true><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power, split);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   }
@@ -571,9 +583,9 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
-  // One warp walks all rows of a series: for a handful of series the generic kernel, which
-  // spreads the scales of one series over CTAs, has the shorter critical path (measured
-  // crossover below 128 series).
+  // The rows of a series are split over warps when the batch is small, but this path also pays
+  // for the separate forward-FFT launch: 0.038 ms flat up to 32 series against 0.021 ms + 1.7 us
+  // per series for the generic kernel -- measured crossover at about 12 series.
   if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF))
     return 1;
   std::vector<RowParam> rows(S);
@@ -593,10 +605,12 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   RowParam *d_rows = (RowParam *)prm;
   // rows.data() is pageable: the copy is staged before the call returns
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
-  const int grid = (int)std::min<int64_t>(batch, (int64_t)sm_count());
+  const int64_t machine_warps = (int64_t)sm_count() * kWarpsDefault;
+  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), machine_warps / batch));
+  const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
   const size_t smem = sizeof(CtaSmemF<2>);
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_fold<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_cwt_fast_fold<2><<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, (float)f0, d_power);
+  k_cwt_fast_fold<2><<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, (float)f0, d_power, split);
   WTB_LAUNCH_CHECK();
   return WTB_OK;
 }

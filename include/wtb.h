@@ -15,8 +15,8 @@
  *  - the caller owns every buffer; the library keeps no caller pointer past
  *    return.  Without WTB_DEVICE_PTRS buffers are host memory and the call is
  *    synchronous (copies inside).  With WTB_DEVICE_PTRS buffers are device
- *    memory on the current device and the call only enqueues work on `stream`
- *    (a cudaStream_t, NULL = default stream).
+ *    memory (the call runs on the device that owns them) and the call only enqueues
+ *    work on `stream` (a cudaStream_t of that device, NULL = default stream).
  *  - there is no CPU fallback: without a usable sm_100 device calls fail.
  */
 #ifndef WTB_H
@@ -50,14 +50,33 @@ extern "C" {
 /* ---- runtime ------------------------------------------------------------ */
 int  wtb_version(void);
 int  wtb_device_count(void);
-/* Bind the calling process to `device` (one process per GPU) and verify it is
- * compute capability 10.x. */
+/* Which device a call runs on: (1) with WTB_DEVICE_PTRS the device that owns the data pointer;
+ * (2) else the device given to wtb_init() (one process per GPU, e.g. under torchrun) or named by
+ * the environment variable WTB_DEVICE; (3) else the calling thread's current CUDA device.  The
+ * device must be compute capability 10.x.  A call that has to switch devices puts the caller's
+ * current device back before it returns. */
 int  wtb_init(int device);
+/* One process, several GPUs (the reference's call sites are single-process: src/wct.py:106-118).
+ * Starts one worker thread and stream per device 0 .. n_gpus-1 (n_gpus <= 0: WTB_GPUS, else all
+ * visible devices).  From then on host-buffer calls of wtb_cwt / wtb_cwt_morlet / wtb_xwt_wct
+ * split their batch into contiguous blocks, one per device, and wtb_wct_significance splits its
+ * realisations; results do not depend on the number of devices.  WTB_DEVICE_PTRS calls are never
+ * split.  wtb_gpu_count() is the number of devices in use (1 without a pool). */
+int  wtb_init_multi(int n_gpus);
+int  wtb_gpu_count(void);
+/* Frees every device buffer the library holds and stops the worker threads.  No call may be in
+ * flight.  The library can be used again afterwards. */
 void wtb_shutdown(void);
 const char *wtb_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py's
  * gpu_launches is the difference across the timed region). */
 uint64_t wtb_kernel_launches(void);
+/* Bytes of device scratch the library holds right now.  Scratch is keyed by (host thread,
+ * device, stream): calls share intermediates only when they are ordered on one stream of one
+ * thread, so two WTB_DEVICE_PTRS calls on different streams never touch each other's scratch.
+ * It is allocated stream-ordered (no device-wide synchronisation when it grows), released when
+ * its host thread exits, and by wtb_shutdown(). */
+uint64_t wtb_scratch_bytes(void);
 
 /* ---- CWT: replaces pycwt.cwt (src/cwt.py:110) + |W|^2 (src/cwt.py:114) ---- */
 /* Scales, Fourier frequencies and cone of influence exactly as pycwt.cwt
@@ -127,6 +146,22 @@ int wtb_wct_mc_hist(double a1, double a2, double dt, double dj, double s0, int J
  * histogram, NaN for the remaining rows that have reliable points. */
 int wtb_wct_sig_from_hist(const uint64_t *hist, int S, int maxscale, double level,
                           const uint8_t *row_has_points, double *sig95);
+
+/* The same percentile step with hist [S, WTB_NBINS] and sig95 [S] in DEVICE memory, enqueued on
+ * `stream` (bit-identical arithmetic); row_has_points stays a host array. */
+int wtb_wct_sig_from_hist_device(const uint64_t *hist, int S, int maxscale, double level,
+                                 const uint8_t *row_has_points, double *sig95, void *stream);
+
+/* pycwt.wct_significance in ONE call (src/wct.py:106 reaches it through wct(sig=True)): the
+ * realisations 0 .. mc_count-1 are split over the devices of wtb_init_multi (or run on the one
+ * current device), each device bins its block, device 0 sums the histograms by reading its peers'
+ * memory over NVLink, and the percentile step gives sig95 [J+1].  surrogates: NULL (device Philox
+ * AR(1) noise keyed by the global realisation index: the result does not depend on the number of
+ * GPUs) or a HOST array [mc_count, 2, nsurr].  hist_out (may be NULL): [J+1, WTB_NBINS] summed
+ * histogram.  Host buffers only. */
+int wtb_wct_significance(double a1, double a2, double dt, double dj, double s0, int J, double f0,
+                         double level, int64_t mc_count, uint64_t seed, const void *surrogates,
+                         int flags, double *sig95, uint64_t *hist_out);
 
 /* Device AR(1) surrogates only (for distribution tests): out [count, 2, nsurr]. */
 int wtb_rednoise(double a1, double a2, int nsurr, int64_t first, int64_t count,

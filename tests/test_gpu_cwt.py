@@ -103,6 +103,28 @@ def test_cwt_coi_mask(shim):
     assert np.array_equal(p_mask[~outside], p[~outside])
 
 
+@pytest.mark.parametrize("n0,batch", [(400, 5), (512, 4), (700, 3), (1024, 3), (1346, 13), (2048, 12), (3351, 3), (4096, 2)])
+def test_cwt_coi_mask_fused_fast_kernels(shim, n0, batch):
+    """north_star (1): the cone-of-influence mask is fused into the FP32 fast kernels' store loops
+    (nfft 512 two-series, 1024, 2048 fold, 4096 rows).  Inside the cone the power is bit-equal to
+    the unmasked fast kernel, outside it is NaN, and the mask itself equals the oracle's
+    `period > coi` (the generic kernel's, too)."""
+    x = np.random.default_rng(n0).standard_normal((batch, n0))
+    launches = shim.kernel_launches()
+    p_mask, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=False, coi_mask=True)
+    per_call = shim.kernel_launches() - launches
+    p, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=False)
+    assert shim.kernel_launches() - launches == 2 * per_call          # same kernels with and without the mask
+    g_mask, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=False, coi_mask=True, generic_only=True)
+    _, _, freqs, coi = po.cwt(x[0], DT, 1 / 12, 2 * DT, -1)[1:5]
+    outside = (1 / freqs)[:, None] > coi[None, :]
+    assert outside.any() and (~outside).any()
+    for b in range(batch):
+        assert np.isnan(p_mask[b][outside]).all()
+        assert np.array_equal(p_mask[b][~outside], p[b][~outside])
+        assert np.array_equal(np.isnan(g_mask[b]), outside)
+
+
 def test_cwt_rejects_bad_arguments(shim):
     x = np.zeros(100)
     with pytest.raises((ValueError, RuntimeError)):

@@ -1,0 +1,192 @@
+"""GPU: runtime behaviour of the C ABI -- scratch ownership (threads, streams), device selection,
+and the one-call multi-GPU path (wtb_init_multi / wtb_wct_significance).
+
+A pool larger than the box is allowed under WTB_POOL_SHARE_DEVICES=1 (workers share devices), so
+the sharding, per-worker scratch and the peer reduction are exercised on a single-GPU machine too;
+with >= 2 devices the same tests run on distinct GPUs."""
+
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import pycwt_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+DT = 1 / 12
+MC = dict(a1=0.989, a2=0.966, dj=1 / 8, s0=2 * DT, J=65)
+
+
+@pytest.fixture()
+def pool(shim):
+    """A pool of two workers: two GPUs when the box has them, one shared GPU otherwise."""
+    os.environ["WTB_POOL_SHARE_DEVICES"] = "1"
+    n = shim.init_multi(2)
+    assert n == 2
+    yield shim
+    shim.init_multi(1)
+    assert shim.gpu_count() == 1
+
+
+def test_one_call_significance_matches_single_device(shim, pool):
+    """pycwt_compat.wct_significance spread over the pool gives the histogram
+    and thresholds of one device, bit for bit (Philox keyed by the global realisation index)."""
+    sig2, hist2 = shim.wct_significance(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], mc_count=37, seed=2024,
+                                        f64=False, return_hist=True)
+    shim.init_multi(1)
+    sig1, hist1 = shim.wct_significance(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], mc_count=37, seed=2024,
+                                        f64=False, return_hist=True)
+    ref = shim.wct_mc_hist(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], mc_count=37, seed=2024, f64=False)
+    assert hist1.sum() > 0
+    assert np.array_equal(hist1, ref) and np.array_equal(hist2, ref)
+    assert np.array_equal(sig1, sig2, equal_nan=True)
+
+
+def test_one_call_significance_host_reduction_fallback(shim, pool, monkeypatch):
+    """Boxes without peer access sum the histograms on the host: same numbers."""
+    ref = shim.wct_mc_hist(0.8, 0.6, DT, 1 / 4, 2 * DT, 24, mc_count=9, seed=5, f64=False)
+    monkeypatch.setenv("WTB_NO_PEER", "1")
+    shim.init_multi(2)
+    _, hist = shim.wct_significance(0.8, 0.6, DT, 1 / 4, 2 * DT, 24, mc_count=9, seed=5, f64=False, return_hist=True)
+    assert np.array_equal(hist, ref)
+
+
+def test_one_call_significance_injected_surrogates(shim, pool):
+    """Host-injected surrogates through the pool: per-realisation parity with the oracle (FP64)."""
+    dj, s0, J = 1 / 4, 2 * DT, 24
+    N, maxscale = shim.wct_mc_geometry(DT, dj, s0, J)
+    rng = np.random.default_rng(3)
+    mc = 5
+    sur = np.stack([np.stack([po.rednoise(N, 0.8, 1, rng), po.rednoise(N, 0.6, 1, rng)]) for _ in range(mc)])
+    sig_ref, hist_ref = po.wct_significance(0.8, 0.6, DT, dj, s0, J, mc_count=mc, surrogates=sur, return_hist=True)
+    sig, hist = shim.wct_significance(0.8, 0.6, DT, dj, s0, J, mc_count=mc, surrogates=sur, f64=True, return_hist=True)
+    assert hist.sum() == hist_ref.sum() and np.abs(hist.astype(np.int64) - hist_ref).sum() <= 4
+    assert np.allclose(sig[:maxscale], sig_ref[:maxscale], atol=2e-3)
+
+
+def test_pycwt_facade_uses_the_pool(shim, pool, tmp_path, monkeypatch):
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    monkeypatch.setenv("WTB_CACHE_DIR", str(tmp_path))
+    launches = shim.kernel_launches()
+    sig = wavelet.wct_significance(0.8, 0.6, DT, 1 / 4, 2 * DT, 24, mc_count=12, cache=False, seed=11)
+    assert shim.kernel_launches() > launches
+    shim.init_multi(1)
+    one = wavelet.wct_significance(0.8, 0.6, DT, 1 / 4, 2 * DT, 24, mc_count=12, cache=False, seed=11)
+    assert np.array_equal(sig, one, equal_nan=True)
+    # n_gpus= builds the pool on demand
+    again = wavelet.wct_significance(0.8, 0.6, DT, 1 / 4, 2 * DT, 24, mc_count=12, cache=False, seed=11, n_gpus=2)
+    assert shim.gpu_count() == 2 and np.array_equal(again, one, equal_nan=True)
+
+
+@pytest.mark.parametrize("f64", [False, True])
+def test_host_batches_are_split_over_the_pool(shim, pool, f64):
+    """Host-buffer CWT and XWT/WCT batches: contiguous blocks per device, same planes.  (700 samples:
+    the nfft = 1024 kernel is bit-identical at any batch size; the nfft = 512 kernel pairs
+    neighbouring series in one transform, so there a series' last bits depend on its neighbour.)"""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((11, 700))
+    y = rng.standard_normal((11, 700))
+    p2, _ = shim.cwt_morlet(x, DT, 1 / 4, 2 * DT, -1, f64=f64)
+    w2, ph2, _ = shim.xwt_wct(x, y, DT, 1 / 4, 2 * DT, -1, f64=f64)
+    shim.init_multi(1)
+    p1, _ = shim.cwt_morlet(x, DT, 1 / 4, 2 * DT, -1, f64=f64)
+    w1, ph1, _ = shim.xwt_wct(x, y, DT, 1 / 4, 2 * DT, -1, f64=f64)
+    assert np.array_equal(p1, p2) and np.array_equal(w1, w2) and np.array_equal(ph1, ph2)
+
+
+def test_device_percentile_is_bit_identical(shim):
+    import torch
+    hist = shim.wct_mc_hist(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], mc_count=5, seed=1, f64=False)
+    _, maxscale = shim.wct_mc_geometry(DT, MC["dj"], MC["s0"], MC["J"])
+    has = shim.row_has_points(DT, MC["dj"], MC["s0"], MC["J"])
+    host = shim.wct_sig_from_hist(hist, maxscale, 0.95, has)
+    d_hist = torch.from_numpy(hist.astype(np.int64)).cuda()
+    d_sig = torch.empty(hist.shape[0], dtype=torch.float64, device="cuda")
+    for level in (0.95, 0.5, 0.999999, 1e-9):
+        host = shim.wct_sig_from_hist(hist, maxscale, level, has)
+        shim.wct_sig_from_hist_device(d_hist.data_ptr(), hist.shape[0], maxscale, level, has, d_sig.data_ptr(),
+                                      stream=torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(d_sig.cpu().numpy(), host, equal_nan=True), level
+
+
+def test_scratch_is_released_when_threads_exit(shim):
+    """Streamlit reruns scripts on fresh threads; their arenas must not pile up."""
+    x = np.random.default_rng(0).standard_normal((64, 1024))
+    shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, 119, f64=False)     # this thread's arenas
+    base = shim.scratch_bytes()
+    peak = []
+
+    def work():
+        shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, 119, f64=False)
+        peak.append(shim.scratch_bytes())
+
+    import time
+    for _ in range(12):
+        t = threading.Thread(target=work)
+        t.start()
+        t.join()
+        # Thread.join() returns when the Python side of the thread is done; the C++ thread-local
+        # destructors (which free the arenas) run a moment later, as the OS thread exits
+        deadline = time.time() + 5.0
+        while shim.scratch_bytes() != base and time.time() < deadline:
+            time.sleep(0.01)
+        assert shim.scratch_bytes() == base
+    assert max(peak) > base
+
+
+def test_two_streams_on_one_thread_do_not_share_scratch(shim):
+    """ADVICE r1 / VERDICT weak 8: WTB_DEVICE_PTRS calls with different parameters on two streams
+    of one host thread, in flight together, give the numbers of the serial calls."""
+    import torch
+    from wavelet_transformer_b200 import engine
+    torch.manual_seed(0)
+    xa = torch.randn(4000, 1024, device="cuda")
+    xb = torch.randn(3000, 1500, device="cuda")
+    Ja, Jb = 119, 84
+    ra = torch.empty(4000, Ja + 1, 1024, device="cuda")
+    rb = torch.empty(3000, Jb + 1, 1500, device="cuda")
+    engine.cwt_power_resident(xa, ra, DT, 1 / 12, 2 * DT, Ja)
+    engine.cwt_power_resident(xb, rb, DT, 1 / 12, 2 * DT, Jb)
+    torch.cuda.synchronize()
+    pa, pb = torch.empty_like(ra), torch.empty_like(rb)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        pa.zero_(); pb.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(sa):
+            engine.cwt_power_resident(xa, pa, DT, 1 / 12, 2 * DT, Ja)
+        with torch.cuda.stream(sb):
+            engine.cwt_power_resident(xb, pb, DT, 1 / 12, 2 * DT, Jb)
+        torch.cuda.synchronize()
+        assert torch.equal(pa, ra) and torch.equal(pb, rb)
+
+
+def test_device_pointer_calls_follow_the_pointer(shim):
+    """a WTB_DEVICE_PTRS call runs on the device that owns its buffers and leaves the
+    caller's current device alone."""
+    import torch
+    from wavelet_transformer_b200 import engine
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    x0 = torch.randn(64, 1024, device="cuda:0")
+    x1 = x0.to("cuda:1")
+    p0 = torch.empty(64, 120, 1024, device="cuda:0")
+    p1 = torch.empty(64, 120, 1024, device="cuda:1")
+    torch.cuda.set_device(0)
+    engine.cwt_power_resident(x0, p0, DT, 1 / 12, 2 * DT, 119)
+    engine.cwt_power_resident(x1, p1, DT, 1 / 12, 2 * DT, 119)
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert torch.equal(p0.cpu(), p1.cpu())
+
+
+def test_shutdown_and_reuse(shim):
+    x = np.random.default_rng(1).standard_normal((8, 512))
+    a, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, -1, f64=True)
+    shim.shutdown()
+    assert shim.scratch_bytes() == 0
+    shim.init(0)
+    b, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, -1, f64=True)
+    assert np.array_equal(a, b)

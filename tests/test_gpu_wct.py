@@ -49,8 +49,9 @@ def test_wct_fp32_batch(shim, dj):
     wct, phase, _ = shim.xwt_wct(y1, y2, DT, dj, 2 * DT, -1, f64=False)
     for b in range(4):
         WCT = po.wct(y1[b], y2[b], DT, dj=dj, s0=2 * DT, J=-1, sig=False, normalize=False)[0]
-        assert np.abs(wct[b] - WCT).max() <= 2e-3, np.abs(wct[b] - WCT).max()  # ratio of FP32 fields
-        assert np.abs(wct[b] - WCT).mean() <= 1e-4
+        ok, worst = normwise_close(wct[b], WCT, 1e-4)      # BASELINE.md FP32 gate: 1e-4 |b| + 1e-4 max|b|
+        assert ok, worst
+        assert np.abs(wct[b] - WCT).mean() <= 2e-6        # measured 2e-7 .. 5e-7 (profiles/r2_wct_fp32_error.jsonl)
 
 
 def test_wct_self_coherence_is_one(shim):
@@ -162,8 +163,10 @@ def test_wct_fp32_n4096_fast_path(shim):
         for got in (w12[b], w12_g[b]):
             assert np.abs(got - ref12).max() <= 1e-4 * np.abs(ref12).max()
         for got in (wct[b], wct_g[b]):
-            assert np.abs(got - WCT).max() <= 2e-3 and np.abs(got - WCT).mean() <= 1e-4
-    assert np.abs(wct - wct_g).max() <= 2e-3
+            ok, worst = normwise_close(got, WCT, 1e-4)     # measured max 6e-6 on this shape
+            assert ok, worst
+            assert np.abs(got - WCT).mean() <= 2e-6
+    assert np.abs(wct - wct_g).max() <= 1e-4
 
 
 def test_mc_cfg5_shape_fast_vs_generic_vs_oracle(shim):
@@ -226,4 +229,5 @@ def test_wct_fp32_fast_path_fuzz(shim):
         ref, _, ref12 = shim.xwt_wct(y1, y2, dt, dj, s0, J, f0, f64=True, want_w12=True, generic_only=True)
         tag = f"n0={n0} dt={dt} dj={dj:.4f} s0={s0} f0={f0} J={J}"
         assert np.abs(w12 - ref12).max() <= 1e-4 * np.abs(ref12).max(), tag
-        assert np.abs(wct - ref).max() <= 5e-3 and np.abs(wct - ref).mean() <= 1e-4, tag
+        ok, worst = normwise_close(wct, ref, 1e-4)
+        assert ok and np.abs(wct - ref).mean() <= 5e-6, (tag, worst)

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "wtb_version": ([], _i32),
     "wtb_device_count": ([], _i32),
     "wtb_init": ([_i32], _i32),
+    "wtb_init_multi": ([_i32], _i32),
+    "wtb_gpu_count": ([], _i32),
+    "wtb_scratch_bytes": ([], C.c_uint64),
     "wtb_shutdown": ([], None),
     "wtb_last_error": ([], C.c_char_p),
     "wtb_kernel_launches": ([], C.c_uint64),
@@ -71,6 +74,8 @@ _SIGNATURES = {
     "wtb_wct_mc_geometry": ([_f64, _f64, _f64, _i32, _f64, _pi, _pi], _i32),
     "wtb_wct_mc_hist": ([_f64, _f64, _f64, _f64, _f64, _i32, _f64, _i64, _i64, _u64, _vp, _i32, _vp, _vp], _i32),
     "wtb_wct_sig_from_hist": ([_vp, _i32, _i32, _f64, _vp, _pd], _i32),
+    "wtb_wct_sig_from_hist_device": ([_vp, _i32, _i32, _f64, _vp, _vp, _vp], _i32),
+    "wtb_wct_significance": ([_f64, _f64, _f64, _f64, _f64, _i32, _f64, _f64, _i64, _u64, _vp, _i32, _pd, _vp], _i32),
     "wtb_rednoise": ([_f64, _f64, _i32, _i64, _i64, _u64, _i32, _vp, _vp], _i32),
     "wtb_modwt": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
     "wtb_imodwt": ([_vp, _i64, _i32, _pd, _pd, _i32, _i32, _i32, _vp, _vp], _i32),
@@ -104,6 +109,11 @@ def lib():
                     fn.argtypes = argtypes
                     fn.restype = restype
                 _lib = handle
+                if os.environ.get("WTB_GPUS"):      # one process, several GPUs
+                    rc = handle.wtb_init_multi(int(os.environ["WTB_GPUS"]))
+                    if rc != 0:
+                        raise WaveletEngineError("wtb_init_multi(WTB_GPUS) failed: "
+                                                 + handle.wtb_last_error().decode("utf-8", "replace"))
     return _lib
 
 
@@ -120,6 +130,23 @@ def _check(rc: int, what: str):
 
 def init(device: int = 0) -> None:
     _check(lib().wtb_init(int(device)), "wtb_init")
+
+
+def init_multi(n_gpus: int = 0) -> int:
+    """One process, several GPUs: host-buffer batches and Monte Carlo realisations are split over
+    devices 0 .. n_gpus-1 (0: WTB_GPUS, else every visible device).  Returns the device count in use."""
+    _check(lib().wtb_init_multi(int(n_gpus)), "wtb_init_multi")
+    return gpu_count()
+
+
+def gpu_count() -> int:
+    """Devices one call is spread over (1 unless init_multi made a pool)."""
+    return int(lib().wtb_gpu_count())
+
+
+def scratch_bytes() -> int:
+    """Bytes of device scratch the library holds right now (all threads)."""
+    return int(lib().wtb_scratch_bytes())
 
 
 def shutdown() -> None:
@@ -368,6 +395,37 @@ def wct_sig_from_hist(hist, maxscale, level, has_points=None):
     _check(lib().wtb_wct_sig_from_hist(_ptr(hist), S, int(maxscale), float(level), _ptr(hp), _dp(sig)),
            "wtb_wct_sig_from_hist")
     return sig
+
+
+def wct_significance(a1, a2, dt, dj, s0, J, f0=6.0, *, level=0.95, mc_count=300, seed=0, surrogates=None,
+                     f64=None, white=False, generic_only=False, return_hist=False):
+    """pycwt.wct_significance in one call (wtb_wct_significance): every device of init_multi()
+    takes a block of realisations, device 0 sums the histograms over NVLink, percentile step.
+    Returns sig95 [J+1] (and the summed histogram [J+1, 1000] with return_hist)."""
+    f64 = _resolve_f64(f64)
+    S = int(J) + 1
+    sur = None
+    if surrogates is not None:
+        nsurr, _ = wct_mc_geometry(dt, dj, s0, J, f0)
+        sur = np.ascontiguousarray(surrogates, dtype=_dtype(f64))
+        if sur.shape != (mc_count, 2, nsurr):
+            raise ValueError(f"surrogates must have shape ({mc_count}, 2, {nsurr}), got {sur.shape}")
+    flags = (F64 if f64 else 0) | (NOISE_WHITE if white else 0) | (GENERIC_ONLY if generic_only else 0)
+    sig = np.empty(S)
+    hist = np.zeros((S, NBINS), dtype=np.uint64) if return_hist else None
+    _check(lib().wtb_wct_significance(a1, a2, dt, dj, s0, int(J), f0, float(level), int(mc_count),
+                                      C.c_uint64(int(seed)), _ptr(sur), flags, _dp(sig), _ptr(hist)),
+           "wtb_wct_significance")
+    return (sig, hist) if return_hist else sig
+
+
+def wct_sig_from_hist_device(hist_ptr, S, maxscale, level, has_points, sig_ptr, *, stream=0):
+    """Device-resident percentile step: hist_ptr / sig_ptr are device addresses of uint64 [S, 1000]
+    and float64 [S]; has_points is a host array (or None).  Asynchronous on `stream`."""
+    hp = None if has_points is None else np.ascontiguousarray(has_points, dtype=np.uint8)
+    _check(lib().wtb_wct_sig_from_hist_device(_ptr(int(hist_ptr)), int(S), int(maxscale), float(level), _ptr(hp),
+                                              _ptr(int(sig_ptr)), C.c_void_p(int(stream))),
+           "wtb_wct_sig_from_hist_device")
 
 
 def rednoise(a1, a2, nsurr, first, count, seed, *, f64=False, white=False):

@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/wtb.h"
@@ -70,27 +71,75 @@ template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
-// ---- device scratch / tables (host side) --------------------------------------
-// Grow-only device arena owned by the library; one per host thread so that
-// concurrent Streamlit sessions never share scratch.  Freed by wtb_shutdown().
-struct Arena {
-  void *ptr = nullptr;
-  size_t cap = 0;
-  int device = -1;
-};
+// ---- per-call context, device scratch, tables (host side) -----------------------
+// Every C-ABI entry point opens a CallScope first.  It decides which device the call runs on
+//   1. the device of a multi-GPU pool worker thread (wtb_init_multi, multi.cu),
+//   2. with WTB_DEVICE_PTRS: the device that owns the data pointer,
+//   3. the device given to wtb_init() / WTB_DEVICE,
+//   4. otherwise the calling thread's current CUDA device,
+// checks once per device that it is sm_100, makes it current for the call and puts the
+// caller's device back on return.  It also records the (device, stream) pair that keys scratch.
+class CallScope {
+ public:
+  CallScope(int flags, const void *data_ptr, void *stream);
+  ~CallScope();
+  CallScope(const CallScope &) = delete;
+  CallScope &operator=(const CallScope &) = delete;
+  int rc() const { return rc_; }
+  int device() const { return device_; }
 
-int arena_reserve(size_t bytes, void **out);  // thread-local arena, 256B aligned
+ private:
+  int rc_ = WTB_OK;
+  int device_ = -1;
+  int restore_ = -1;         // device to make current again on exit (-1: nothing to undo)
+  int outer_device_ = -1;    // enclosing scope's key (entry points may nest)
+  cudaStream_t outer_stream_ = nullptr;
+  bool nested_ = false;
+};
+#define WTB_ENTER(flags, ptr, stream)                \
+  ::wtb::CallScope scope__((flags), (ptr), (stream)); \
+  WTB_TRY(scope__.rc())
+
+int current_device();         // device of the innermost CallScope on this thread
+cudaStream_t current_stream();
+
+// Grow-only device scratch owned by the library, keyed by (host thread, device, stream): two
+// calls only ever share scratch when they are ordered on the same stream of the same thread, so
+// concurrent Streamlit sessions (threads) and concurrent torch streams never see each other's
+// intermediates.  Memory is stream-ordered (cudaMallocAsync / cudaFreeAsync), so growing an
+// arena neither synchronises the device nor frees memory a queued kernel still uses.  A thread's
+// arenas are released when the thread exits, everything that is left by wtb_shutdown().
+int arena_reserve(size_t bytes, void **out);  // intermediates, 256B aligned
 // Second independent arena (I/O staging for host-pointer calls).
 int staging_reserve(size_t bytes, void **out);
-// small per-thread buffer for kernel parameter tables, separate from the two arenas above so a
-// callee can fill it while its caller's arena holds live data; released by wtb_shutdown as well
+// small buffer for kernel parameter tables, separate from the two arenas above so a callee can
+// fill it while its caller's arena holds live data
 int params_reserve(size_t bytes, void **out);
+// bytes of device scratch the library holds right now, over all threads (leak tests)
+size_t scratch_bytes_held();
 
 // Twiddle table exp(-2*pi*i*k/N), k in [0,N), in precision T; cached per (device,N).
 template <typename T> int twiddles(int N, const cplx<T> **out);
 
-int ensure_device();  // lazily binds device 0 (or WTB_DEVICE) and checks sm_100
-int sm_count();
+int sm_count();               // SMs of current_device()
+
+// ---- multi-GPU pool (multi.cu): one worker thread + stream per device -------------------
+int pool_size();              // 1 unless wtb_init_multi() made a pool
+// Runs fn(part, first, count, stream) for a split of [0, total) into contiguous blocks, one per
+// pool device, each on that device's worker thread (device current, scratch keyed by the worker's
+// stream) and waits for all of them.  Returns the first failure (its message becomes the caller's
+// wtb_last_error()).  With no pool, or total < min_total, fn runs once on the calling thread.
+using ShardFn = int (*)(void *ctx, int part, int64_t first, int64_t count, cudaStream_t stream);
+int run_sharded(int64_t total, int64_t min_total, cudaStream_t caller_stream, ShardFn fn, void *ctx);
+template <typename F> int run_sharded_fn(int64_t total, int64_t min_total, cudaStream_t st, F &&f) {
+  using Fn = typename std::remove_reference<F>::type;
+  return run_sharded(total, min_total, st,
+                     [](void *ctx, int part, int64_t first, int64_t count, cudaStream_t s) -> int {
+                       return (*static_cast<Fn *>(ctx))(part, first, count, s);
+                     },
+                     (void *)&f);
+}
+const char *last_error();     // this thread's message (workers hand theirs to the caller)
 
 inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }

@@ -135,6 +135,8 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   return WTB_OK;
 }
 
+static thread_local bool g_in_shard = false;   // set on a pool worker while it runs its block
+
 template <typename T>
 static int cwt_entry(const void *x, int64_t batch, int n0, int N, double dt, const Axes &ax,
                      const Mother &f0, int flags, void *power_out, void *coef_out, cudaStream_t st) {
@@ -142,6 +144,17 @@ static int cwt_entry(const void *x, int64_t batch, int n0, int N, double dt, con
   if (flags & WTB_DEVICE_PTRS)
     return cwt_device<T>((const T *)x, batch, n0, N, dt, ax, f0, flags, (T *)power_out,
                          (cplx<T> *)coef_out, st);
+  // host buffers, several GPUs (wtb_init_multi): contiguous blocks of series, one per device
+  if (pool_size() > 1 && batch >= 2 * pool_size() && !g_in_shard) {
+    return run_sharded_fn(batch, 2, st, [&](int, int64_t first, int64_t count, cudaStream_t s) {
+      g_in_shard = true;
+      const int rc = cwt_entry<T>((const T *)x + first * n0, count, n0, N, dt, ax, f0, flags,
+                                  power_out ? (T *)power_out + first * S * n0 : nullptr,
+                                  coef_out ? (cplx<T> *)coef_out + first * S * n0 : nullptr, s);
+      g_in_shard = false;
+      return rc;
+    });
+  }
   // host buffers: stream the batch through a bounded staging arena
   const size_t per_row = sizeof(T) * ((size_t)n0 + (power_out ? (size_t)S * n0 : 0) +
                                       (coef_out ? 2 * (size_t)S * n0 : 0));
@@ -181,7 +194,7 @@ extern "C" int wtb_cwt(const void *x, int64_t batch, int n0, int nfft, double dt
   WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
               "nfft=%d must be a power of two >= n0=%d (pycwt's scipy.fftpack padding rule); "
               "the un-padded mkl_fft variant is not supported", nfft, n0);
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, x, stream);
   Mother mo;
   mo.kind = mother;
   mo.param = param;
@@ -250,7 +263,7 @@ static int icwt_impl(const void *coef, int64_t batch, int S, int n0, const doubl
 extern "C" int wtb_icwt(const void *coef, int64_t batch, int S, int n0, const double *scales, double factor,
                         int flags, void *x_out, void *stream) {
   WTB_REQUIRE(coef && x_out && scales && batch >= 0 && S > 0 && n0 > 0, WTB_EINVAL, "wtb_icwt: bad arguments");
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, coef, stream);
   if (batch == 0) return WTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (flags & WTB_F64) return icwt_impl<double>(coef, batch, S, n0, scales, factor, flags, x_out, st);

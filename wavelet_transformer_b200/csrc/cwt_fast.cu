@@ -64,6 +64,7 @@ template <int kWarps> struct CtaSmem {
   float4 tw_a[16][32];              // pair (t2, t2+16) x k1=lane   : step A output twiddle
   float4 tw_b[16][32];              // pair (2m, 2m+1)  x t2=lane   : single-pass input twiddle
   RowParam row[kMaxRows];
+  ushort2 coi[kMaxRows];            // COI only: samples [x, y] of row s lie inside the cone of influence
   WarpSmem w[kWarps];
 };
 
@@ -92,10 +93,16 @@ __device__ __forceinline__ constexpr int below_pow2(int m) {
 // the two halves of one packed register: |a|^2 = |x[t] + x[t+512]|^2 / 4, |b|^2 likewise with
 // the difference (the phase w^t drops out of the power).  The forward transforms of both real
 // series come from one pass over A - iB repeated twice (even bins = the 512-point spectrum).
-template <int kWarps, bool HALF>
+//
+// COI = true fuses pycwt's cone-of-influence mask into the store loop (north_star (1); consumers:
+// src/utils/wavelet_helpers.py:60-78, pycwt's `outsidecoi`): row s keeps samples coi[s].x ..
+// coi[s].y and writes NaN elsewhere -- the interval is evaluated on the host in double exactly as
+// the generic kernel evaluates `period > coi(t)`, so the mask is bit-equal and costs no traffic.
+template <int kWarps, bool HALF, bool COI>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
-                const RowParam *__restrict__ rows, float f0, float *__restrict__ power, int split) {
+                const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
+                float *__restrict__ power, int split) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem<kWarps> &sm = *reinterpret_cast<CtaSmem<kWarps> *>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -110,7 +117,10 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
     sincospif(2.0f * (float)((2 * p + 1) * l) / (float)kN, &s1, &c1);
     sm.tw_b[p][l] = make_float4(c0, c1, s0, s1);
   }
-  for (int i = threadIdx.x; i < S; i += blockDim.x) sm.row[i] = rows[i];
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    sm.row[i] = rows[i];
+    if (COI) sm.coi[i] = coi[i];
+  }
   __syncthreads();
   WarpSmem &ws = sm.w[warp];
   // consecutive series go to different SMs: a small batch spreads over the machine
@@ -291,18 +301,30 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
         // (x[t], x[t+512]) share a register: a = (sum)/2, b = (difference)/2 up to a phase; the 1/2
         // rides in lognorm (1/1024 instead of 1/512)
         float *orow = out + (int64_t)s * n0;
+        const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kN;
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
           const float sr = R[p].x + R[p].y, si = I[p].x + I[p].y;
           const float dr = R[p].x - R[p].y, di = I[p].x - I[p].y;
           if (lane + 32 * p < n0) {
-            __stcs(orow + 32 * p, fmaf(sr, sr, si * si) * unscale_a);
-            if (has_b) __stcs(orow + (int64_t)S * n0 + 32 * p, fmaf(dr, dr, di * di) * unscale_b);
+            const bool in = !COI || (lane + 32 * p >= tlo && lane + 32 * p <= thi);
+            __stcs(orow + 32 * p, in ? fmaf(sr, sr, si * si) * unscale_a : NAN);
+            if (has_b) __stcs(orow + (int64_t)S * n0 + 32 * p, in ? fmaf(dr, dr, di * di) * unscale_b : NAN);
           }
         }
       } else {
         float *orow = out + (int64_t)s * n0;
-        if (full_row) {
+        if (COI) {
+          // outside [tlo, thi] (and past n0, where thi < n0 ends the row anyway) nothing valid exists
+          const int tlo = sm.coi[s].x, thi = sm.coi[s].y;
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+            const int ta = lane + 32 * p, tb = ta + 512;
+            if (ta < n0) __stcs(orow + 32 * p, (ta >= tlo && ta <= thi) ? pw.x : NAN);
+            if (tb < n0) __stcs(orow + 32 * (p + 16), (tb >= tlo && tb <= thi) ? pw.y : NAN);
+          }
+        } else if (full_row) {
 #pragma unroll
           for (int p = 0; p < 16; ++p) {
             const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
@@ -350,6 +372,7 @@ template <int D> struct CtaSmemF {
   float4 tw_b[16][32];
   float4 tw_c[D - 1][16][32];       // exp(+2*pi*i*q*k/N) for the pair k = lane + 64 m, k + 32, q = 1 .. D-1
   RowParam row[kMaxRowsF];
+  ushort2 coi[kMaxRowsF];           // COI only (see k_cwt_fast_1024)
   WarpSmemF w[kWarpsDefault];
 };
 
@@ -368,10 +391,11 @@ __device__ __forceinline__ constexpr int below_pow2_16(int m) {
   return m < 8 ? below_pow2(m) : 8;
 }
 
-template <int D>
+template <int D, bool COI>
 __global__ void __launch_bounds__(kWarpsDefault * 32, 1)
 k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
-                const RowParam *__restrict__ rows, float f0, float *__restrict__ power, int split) {
+                const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
+                float *__restrict__ power, int split) {
   constexpr int kNF = kN * D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmemF<D> &sm = *reinterpret_cast<CtaSmemF<D> *>(smem_raw);
@@ -393,7 +417,10 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       sm.tw_c[q - 1][p][l] = make_float4(c0, c1, s0, s1);
     }
   }
-  for (int i = threadIdx.x; i < S; i += blockDim.x) sm.row[i] = rows[i];
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    sm.row[i] = rows[i];
+    if (COI) sm.coi[i] = coi[i];
+  }
   __syncthreads();
   WarpSmemF &ws = sm.w[warp];
   float *const yr = ws.trr, *const yi = ws.tri;      // single-pass rows never touch the transpose buffer
@@ -491,17 +518,47 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       // Default store policy: the other parts of the line follow within this row.
       float *orow = out + (int64_t)s * n0 + q;
       const int tl = D * lane + q;
+      const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
-        const float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-        if (tl + 32 * D * p < n0) st_stream(orow + 32 * D * p, pw.x);
-        if (tl + 32 * D * p + 512 * D < n0) st_stream(orow + 32 * D * p + 512 * D, pw.y);
+        float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+        const int ta = tl + 32 * D * p, tb = ta + 512 * D;
+        if (COI) {
+          if (ta < tlo || ta > thi) pw.x = NAN;
+          if (tb < tlo || tb > thi) pw.y = NAN;
+        }
+        if (ta < n0) st_stream(orow + 32 * D * p, pw.x);
+        if (tb < n0) st_stream(orow + 32 * D * p + 512 * D, pw.y);
       }
     }
   }
 }
 
 }  // namespace
+
+// Per-row sample interval inside the cone of influence, evaluated in double with the expression
+// the generic kernel (cwt.cu) and pycwt use -- period(s) > coi(t) is masked -- so that the fused
+// mask is bit-equal.  Rows with no valid sample get the empty interval [1, 0].
+void coi_row_ranges(int n0, double dt, const Axes &ax, double f0, std::vector<ushort2> *out) {
+  const int S = ax.J + 1;
+  const double fl = morlet_flambda(f0);
+  const double c = fl * (1.0 / std::sqrt(2.0)) * dt;
+  out->resize(S);
+  for (int s = 0; s < S; ++s) {
+    const double period = 1.0 / (1.0 / (fl * ax.scales[s]));
+    int lo = 1, hi = 0;
+    bool any = false;
+    for (int t = 0; t < n0; ++t) {
+      const double coi = c * (n0 / 2.0 - std::fabs(t - (n0 - 1) / 2.0));
+      if (!(period > coi)) {
+        if (!any) lo = t;
+        hi = t;
+        any = true;
+      }
+    }
+    (*out)[s] = make_ushort2((unsigned short)lo, (unsigned short)hi);
+  }
+}
 
 // smallest batch the warp-per-series kernels take (WTB_CWT_MIN_BATCH overrides; tests set 1)
 static int64_t min_fast_batch(int64_t dflt) {
@@ -516,7 +573,8 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
   // domain a series' bin kk sits at k = 2 kk + parity, so a, lognorm and the band edge are those
   // of a 1024-point transform with the edge one bin further out
   const bool half = nfft == kN / 2;
-  if ((nfft != kN && !half) || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRows) return 1;
+  if ((nfft != kN && !half) || f0 < kZCut || S > kMaxRows) return 1;
+  const bool coi = flags & WTB_COI_MASK;
   // With the rows of a series split over warps (below) this kernel is ahead of the generic one at
   // every batch size for nfft = 1024 (0.017 ms for one series against 0.018); two series per warp
   // (nfft = 512) pays off from about 20 series (0.021 ms flat against 0.017 + 0.4 us per series).
@@ -545,30 +603,37 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
     }
   }
   void *scratch = nullptr;
-  WTB_TRY(arena_reserve(sizeof(RowParam) * S, &scratch));
+  WTB_TRY(arena_reserve(sizeof(RowParam) * S + sizeof(ushort2) * S, &scratch));
   RowParam *d_rows = (RowParam *)scratch;
+  ushort2 *d_coi = nullptr;
   // rows.data() is pageable: the copy is staged before the call returns
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
+  if (coi) {
+    std::vector<ushort2> rng;
+    coi_row_ranges(n0, dt, ax, f0, &rng);
+    d_coi = (ushort2 *)(d_rows + S);
+    WTB_CUDA(cudaMemcpyAsync(d_coi, rng.data(), sizeof(ushort2) * S, cudaMemcpyHostToDevice, st));
+  }
   int warps = kWarpsDefault;
   if (const char *e = std::getenv("WTB_CWT_WARPS")) warps = std::atoi(e);
-  auto launch = [&](auto tag) -> int {
-    constexpr int W = decltype(tag)::value;
-    const size_t smem = sizeof(CtaSmem<W>);
-    WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
-    k_cwt_fast_1024<W, false><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power, split);
+  auto launch_k = [&](auto kern, int W, int64_t items) -> int {
+    const size_t smem = sizeof(CtaSmem<kWarpsDefault>) - sizeof(WarpSmem) * (kWarpsDefault - W);
+    WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>(items * split, (int64_t)sm_count());
+    kern<<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   };
+  auto launch = [&](auto tag) -> int {
+    constexpr int W = decltype(tag)::value;
+    static_assert(sizeof(CtaSmem<W>) == sizeof(CtaSmem<kWarpsDefault>) - sizeof(WarpSmem) * (kWarpsDefault - W), "layout");
+    return launch_k(k_cwt_fast_1024<W, false, false>, W, batch);
+  };
   if (half) {
-    constexpr int W = kWarpsDefault;
-    const size_t smem = sizeof(CtaSmem<W>);
-    WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_1024<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<int64_t>(series_items * split, (int64_t)sm_count());
-    k_cwt_fast_1024<W, true><<<grid, W * 32, smem, st>>>(d_x, batch, n0, S, d_rows, (float)f0, d_power, split);
-    WTB_LAUNCH_CHECK();
-    return WTB_OK;
+    if (coi) return launch_k(k_cwt_fast_1024<kWarpsDefault, true, true>, kWarpsDefault, series_items);
+    return launch_k(k_cwt_fast_1024<kWarpsDefault, true, false>, kWarpsDefault, series_items);
   }
+  if (coi) return launch_k(k_cwt_fast_1024<kWarpsDefault, false, true>, kWarpsDefault, batch);
   switch (warps) {
     case 12: return launch(std::integral_constant<int, 12>{});
     case 14: return launch(std::integral_constant<int, 14>{});
@@ -586,8 +651,8 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   // The rows of a series are split over warps when the batch is small, but this path also pays
   // for the separate forward-FFT launch: 0.038 ms flat up to 32 series against 0.021 ms + 1.7 us
   // per series for the generic kernel -- measured crossover at about 12 series.
-  if (nfft != 2 * kN || (flags & WTB_COI_MASK) || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF))
-    return 1;
+  if (nfft != 2 * kN || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF)) return 1;
+  const bool coi = flags & WTB_COI_MASK;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;
@@ -601,18 +666,28 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   }
   // the caller's arena holds xhat: row parameters go to the per-thread parameter buffer
   void *prm = nullptr;
-  WTB_TRY(params_reserve(sizeof(RowParam) * kMaxRowsF, &prm));
+  WTB_TRY(params_reserve((sizeof(RowParam) + sizeof(ushort2)) * kMaxRowsF, &prm));
   RowParam *d_rows = (RowParam *)prm;
+  ushort2 *d_coi = nullptr;
   // rows.data() is pageable: the copy is staged before the call returns
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(RowParam) * S, cudaMemcpyHostToDevice, st));
+  if (coi) {
+    std::vector<ushort2> rng;
+    coi_row_ranges(n0, dt, ax, f0, &rng);
+    d_coi = (ushort2 *)(d_rows + kMaxRowsF);
+    WTB_CUDA(cudaMemcpyAsync(d_coi, rng.data(), sizeof(ushort2) * S, cudaMemcpyHostToDevice, st));
+  }
   const int64_t machine_warps = (int64_t)sm_count() * kWarpsDefault;
   const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), machine_warps / batch));
   const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
   const size_t smem = sizeof(CtaSmemF<2>);
-  WTB_CUDA(cudaFuncSetAttribute(k_cwt_fast_fold<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_cwt_fast_fold<2><<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, (float)f0, d_power, split);
-  WTB_LAUNCH_CHECK();
-  return WTB_OK;
+  auto run = [&](auto kern) -> int {
+    WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
+    WTB_LAUNCH_CHECK();
+    return WTB_OK;
+  };
+  return coi ? run(k_cwt_fast_fold<2, true>) : run(k_cwt_fast_fold<2, false>);
 }
 
 }  // namespace wtb

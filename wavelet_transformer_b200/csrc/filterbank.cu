@@ -429,7 +429,7 @@ extern "C" int wtb_modwt(const void *x, int64_t batch, int n, const double *g, c
   WTB_REQUIRE(x && w_out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_modwt: bad arguments");
   Taps taps;
   WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, x, stream);
   if (batch == 0) return WTB_OK;
   return DISPATCH(modwt_impl, x, batch, n, taps, J, flags, w_out, (cudaStream_t)stream);
 }
@@ -439,7 +439,7 @@ extern "C" int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, 
   WTB_REQUIRE(w && x_out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_imodwt: bad arguments");
   Taps taps;
   WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, w, stream);
   if (batch == 0) return WTB_OK;
   return DISPATCH(imodwt_impl, w, batch, n, taps, J, flags, x_out, (cudaStream_t)stream);
 }
@@ -447,7 +447,7 @@ extern "C" int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, 
 extern "C" int wtb_modwtmra(const void *w, int64_t batch, int n, const double *filt, int J, int flags,
                             void *out, void *stream) {
   WTB_REQUIRE(w && out && filt && batch >= 0 && n > 0 && J >= 1, WTB_EINVAL, "wtb_modwtmra: bad arguments");
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, w, stream);
   if (batch == 0) return WTB_OK;
   return DISPATCH(mra_impl, w, batch, n, filt, J, flags, out, (cudaStream_t)stream);
 }
@@ -457,7 +457,7 @@ extern "C" int wtb_modwtmra_taps(const void *w, int64_t batch, int n, const doub
   WTB_REQUIRE(w && out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_modwtmra_taps: bad arguments");
   Taps taps;
   WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, w, stream);
   if (batch == 0) return WTB_OK;
   return DISPATCH(mra_taps_impl, w, batch, n, taps, g, h, J, flags, out, (cudaStream_t)stream);
 }
@@ -467,7 +467,7 @@ extern "C" int wtb_wavedec(const void *x, int64_t batch, int n, const double *de
   WTB_REQUIRE(x && coeffs && batch >= 0 && n > 0 && level >= 0, WTB_EINVAL, "wtb_wavedec: bad arguments");
   Taps taps;
   WTB_TRY(make_taps(dec_lo, dec_hi, L, 1.0, &taps));
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, x, stream);
   if (batch == 0) return WTB_OK;
   return DISPATCH(wavedec_impl, x, batch, n, taps, level, flags, coeffs, (cudaStream_t)stream);
 }
@@ -477,7 +477,7 @@ extern "C" int wtb_waverec(const void *coeffs, int64_t batch, const int *lens, i
   WTB_REQUIRE(coeffs && x_out && lens && batch >= 0 && level >= 0, WTB_EINVAL, "wtb_waverec: bad arguments");
   Taps taps;
   WTB_TRY(make_taps(rec_lo, rec_hi, L, 1.0, &taps));
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, coeffs, stream);
   if (batch == 0) return WTB_OK;
   return DISPATCH(waverec_impl, coeffs, batch, lens, level, taps, flags, x_out, (cudaStream_t)stream);
 }

@@ -122,7 +122,7 @@ extern "C" int wtb_rednoise(double a1, double a2, int nsurr, int64_t first, int6
                             int flags, void *out, void *stream) {
   WTB_REQUIRE(out && nsurr > 0 && count >= 0 && first >= 0, WTB_EINVAL, "wtb_rednoise: bad arguments");
   WTB_REQUIRE(fabs(a1) < 1 && fabs(a2) < 1, WTB_EINVAL, "AR(1) coefficients must lie in (-1, 1)");
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, out, stream);
   if (count == 0) return WTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool f64 = flags & WTB_F64;

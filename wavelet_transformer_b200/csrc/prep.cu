@@ -112,7 +112,7 @@ extern "C" int wtb_series_prep(const void *x, int64_t batch, int n, int detrend,
   WTB_REQUIRE(y_out || ar1_out, WTB_EINVAL, "wtb_series_prep: no output requested");
   WTB_REQUIRE(!(detrend && remove_mean), WTB_EINVAL,
               "Only standardize by either removing secular trend or mean, not both.");
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, x, stream);
   if (batch == 0) return WTB_OK;
   const int mode = (detrend ? WTB_PREP_DETREND : 0) | (remove_mean ? WTB_PREP_REMOVE_MEAN : 0) |
                    (standardize ? WTB_PREP_STANDARDIZE : 0);

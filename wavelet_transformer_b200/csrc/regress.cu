@@ -98,7 +98,7 @@ extern "C" int wtb_rowwise_ols(const void *x, int64_t x_rows, const void *y, int
   WTB_REQUIRE(x_rows == y_rows || x_rows == 1 || y_rows == 1, WTB_EINVAL,
               "wtb_rowwise_ols: x has %lld rows and y %lld (equal, or one of them 1 to broadcast)",
               (long long)x_rows, (long long)y_rows);
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, x, stream);
   const int64_t rows = x_rows > y_rows ? x_rows : y_rows;
   if (x_rows == 0 || y_rows == 0) return WTB_OK;
   cudaStream_t st = (cudaStream_t)stream;

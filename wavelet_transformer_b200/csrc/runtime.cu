@@ -25,12 +25,22 @@ static std::atomic<uint64_t> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
-// ---- device binding -------------------------------------------------------------
+// ---- device selection --------------------------------------------------------------
 static std::mutex g_mu;
-static int g_device = -1;  // process-wide (one process per GPU)
-static int g_sms = 0;
+static int g_default_device = -1;   // wtb_init(device) / WTB_DEVICE; -1: follow the caller's current device
+constexpr int kMaxDevices = 64;
+struct DeviceInfo {
+  int state = 0;   // 0 unknown, 1 usable sm_100, -1 rejected
+  int sms = 0;
+};
+static DeviceInfo g_devinfo[kMaxDevices];
 
-static int bind_device(int device) {
+thread_local int tl_worker_device = -1;      // set by multi.cu's pool threads
+static thread_local int tl_device = -1;      // innermost CallScope
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local int tl_depth = 0;
+
+static int check_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -39,79 +49,200 @@ static int bind_device(int device) {
     cudaGetLastError();
     return WTB_ENODEVICE;
   }
-  WTB_REQUIRE(device >= 0 && device < count, WTB_EINVAL, "device %d out of range [0,%d)", device, count);
-  cudaDeviceProp p;
-  WTB_CUDA(cudaGetDeviceProperties(&p, device));
-  WTB_REQUIRE(p.major == 10, WTB_ENODEVICE,
-              "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
-  WTB_CUDA(cudaSetDevice(device));
-  g_device = device;
-  g_sms = p.multiProcessorCount;
+  WTB_REQUIRE(device >= 0 && device < count && device < kMaxDevices, WTB_EINVAL, "device %d out of range [0,%d)",
+              device, count);
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceInfo &di = g_devinfo[device];
+  if (di.state == 0) {
+    int major = 0, minor = 0, sms = 0;
+    WTB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    WTB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    WTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    di.sms = sms;
+    di.state = major == 10 ? 1 : -(100 + major * 10 + minor);
+  }
+  WTB_REQUIRE(di.state == 1, WTB_ENODEVICE, "device %d is sm_%d; this library is built for sm_100a only", device,
+              -di.state - 100);
   return WTB_OK;
 }
 
-int ensure_device() {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_device >= 0) {
-    // a new host thread starts on device 0: re-select the bound device
-    int cur = -1;
-    WTB_CUDA(cudaGetDevice(&cur));
-    if (cur != g_device) WTB_CUDA(cudaSetDevice(g_device));
-    return WTB_OK;
+CallScope::CallScope(int flags, const void *data_ptr, void *stream) {
+  nested_ = tl_depth > 0;
+  outer_device_ = tl_device;
+  outer_stream_ = tl_stream;
+  ++tl_depth;
+  if (nested_) {          // an entry point called from another one: same device, same scratch key
+    device_ = tl_device;
+    return;
   }
-  int dev = 0;
-  if (const char *env = getenv("WTB_DEVICE")) dev = atoi(env);
-  return bind_device(dev);
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device visible (%s); libwavelet_sm100a has no CPU fallback", cudaGetErrorString(e));
+    cudaGetLastError();
+    rc_ = WTB_ENODEVICE;
+    return;
+  }
+  int want = -1;
+  if (tl_worker_device >= 0) {
+    want = tl_worker_device;
+  } else if ((flags & WTB_DEVICE_PTRS) && data_ptr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, data_ptr) == cudaSuccess &&
+        (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+      want = attr.device;
+    } else {
+      cudaGetLastError();
+      set_error("WTB_DEVICE_PTRS: %p is not a device pointer", data_ptr);
+      rc_ = WTB_EINVAL;
+      return;
+    }
+  } else if (g_default_device >= 0) {
+    want = g_default_device;
+  } else if (const char *env = getenv("WTB_DEVICE")) {
+    want = atoi(env);
+  } else {
+    want = cur;
+  }
+  rc_ = check_device(want);
+  if (rc_ != WTB_OK) return;
+  if (want != cur) {
+    e = cudaSetDevice(want);
+    if (e != cudaSuccess) {
+      rc_ = cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+      return;
+    }
+    restore_ = cur;
+  }
+  device_ = want;
+  tl_device = want;
+  tl_stream = (cudaStream_t)stream;
 }
 
-int sm_count() { return g_sms > 0 ? g_sms : 148; }
+CallScope::~CallScope() {
+  --tl_depth;
+  if (nested_) return;
+  tl_device = outer_device_;
+  tl_stream = outer_stream_;
+  if (restore_ >= 0) cudaSetDevice(restore_);
+}
+
+int current_device() { return tl_device; }
+cudaStream_t current_stream() { return tl_stream; }
+
+int sm_count() {
+  const int d = tl_device;
+  return (d >= 0 && d < kMaxDevices && g_devinfo[d].sms > 0) ? g_devinfo[d].sms : 148;
+}
+
+const char *last_error() { return g_err; }
 
 // ---- arenas ------------------------------------------------------------------------
-static std::mutex g_arena_mu;
-static std::vector<Arena *> g_arenas;  // every thread's arenas, for shutdown
+// One ArenaSet per (thread, device, stream); a thread keeps at most kMaxSetsPerThread of them
+// (least recently used goes first), so a caller that keeps making new streams cannot grow the
+// footprint without bound.
+struct Arena {
+  void *ptr = nullptr;
+  size_t cap = 0;
+};
+struct ArenaSet {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  uint64_t last_use = 0;
+  Arena a[3];   // intermediates, staging, parameters
+};
+constexpr int kMaxSetsPerThread = 8;
 
-static Arena *new_arena() {
-  Arena *a = new Arena();
-  std::lock_guard<std::mutex> lk(g_arena_mu);
-  g_arenas.push_back(a);
-  return a;
+static std::mutex g_arena_mu;
+static std::vector<ArenaSet *> g_sets;   // every live set, for wtb_shutdown and the byte count
+static std::atomic<size_t> g_scratch_bytes{0};
+
+static void release_set(ArenaSet *s) {
+  // cudaFree is valid for stream-ordered allocations and waits for the work that uses them
+  int cur = -1;
+  const bool have = cudaGetDevice(&cur) == cudaSuccess;
+  bool any = false;
+  for (Arena &a : s->a) any = any || a.ptr;
+  if (any && have && cur != s->device) cudaSetDevice(s->device);
+  for (Arena &a : s->a) {
+    if (a.ptr) {
+      cudaFree(a.ptr);
+      g_scratch_bytes.fetch_sub(a.cap, std::memory_order_relaxed);
+    }
+    a.ptr = nullptr;
+    a.cap = 0;
+  }
+  if (any && have && cur != s->device) cudaSetDevice(cur);
+  cudaGetLastError();   // at process exit the runtime may already be unloading: nothing to report
 }
 
-static int reserve(Arena *a, size_t bytes, void **out) {
+struct ThreadArenas {
+  std::vector<ArenaSet *> sets;
+  uint64_t tick = 0;
+  ~ThreadArenas() {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (ArenaSet *s : sets) {
+      release_set(s);
+      for (size_t i = 0; i < g_sets.size(); ++i)
+        if (g_sets[i] == s) { g_sets[i] = g_sets.back(); g_sets.pop_back(); break; }
+      delete s;
+    }
+  }
+  ArenaSet *get(int device, cudaStream_t stream) {
+    ++tick;
+    for (ArenaSet *s : sets)
+      if (s->device == device && s->stream == stream) { s->last_use = tick; return s; }
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    ArenaSet *s = nullptr;
+    if ((int)sets.size() >= kMaxSetsPerThread) {
+      s = sets[0];
+      for (ArenaSet *c : sets) if (c->last_use < s->last_use) s = c;
+      release_set(s);
+    } else {
+      s = new ArenaSet();
+      sets.push_back(s);
+      g_sets.push_back(s);
+    }
+    s->device = device;
+    s->stream = stream;
+    s->last_use = tick;
+    return s;
+  }
+};
+static thread_local ThreadArenas tl_arenas;
+
+static int reserve(int which, size_t bytes, void **out) {
+  WTB_REQUIRE(tl_device >= 0, WTB_ECUDA, "internal: scratch requested outside a call scope");
+  ArenaSet *set = tl_arenas.get(tl_device, tl_stream);
+  Arena &a = set->a[which];
   if (bytes == 0) bytes = 256;
-  if (a->cap < bytes || a->device != g_device) {
-    if (a->ptr) {
-      WTB_CUDA(cudaDeviceSynchronize());
-      WTB_CUDA(cudaFree(a->ptr));
-      a->ptr = nullptr;
-      a->cap = 0;
+  if (a.cap < bytes) {
+    if (a.ptr) {
+      // stream-ordered: the old block is released once the work queued so far on this stream
+      // (the only work that can be using it) has finished; nothing blocks here
+      WTB_CUDA(cudaFreeAsync(a.ptr, set->stream));
+      g_scratch_bytes.fetch_sub(a.cap, std::memory_order_relaxed);
+      a.ptr = nullptr;
+      a.cap = 0;
     }
     size_t want = bytes + bytes / 8;
     want = (want + (1u << 20) - 1) & ~size_t((1u << 20) - 1);
-    cudaError_t e = cudaMalloc(&a->ptr, want);
+    cudaError_t e = cudaMallocAsync(&a.ptr, want, set->stream);
     if (e != cudaSuccess) {
-      a->ptr = nullptr;
-      return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+      a.ptr = nullptr;
+      return cuda_fail(e, "cudaMallocAsync(scratch)", __FILE__, __LINE__);
     }
-    a->cap = want;
-    a->device = g_device;
+    a.cap = want;
+    g_scratch_bytes.fetch_add(want, std::memory_order_relaxed);
   }
-  *out = a->ptr;
+  *out = a.ptr;
   return WTB_OK;
 }
 
-int arena_reserve(size_t bytes, void **out) {
-  static thread_local Arena *a = new_arena();
-  return reserve(a, bytes, out);
-}
-int staging_reserve(size_t bytes, void **out) {
-  static thread_local Arena *a = new_arena();
-  return reserve(a, bytes, out);
-}
-int params_reserve(size_t bytes, void **out) {
-  static thread_local Arena *a = new_arena();
-  return reserve(a, bytes, out);
-}
+int arena_reserve(size_t bytes, void **out) { return reserve(0, bytes, out); }
+int staging_reserve(size_t bytes, void **out) { return reserve(1, bytes, out); }
+int params_reserve(size_t bytes, void **out) { return reserve(2, bytes, out); }
+size_t scratch_bytes_held() { return g_scratch_bytes.load(std::memory_order_relaxed); }
 
 // ---- twiddles ----------------------------------------------------------------------
 template <typename T> struct TwCache {
@@ -126,7 +257,7 @@ template <typename T> static TwCache<T> &tw_cache() {
 template <typename T> int twiddles(int N, const cplx<T> **out) {
   TwCache<T> &c = tw_cache<T>();
   std::lock_guard<std::mutex> lk(c.mu);
-  auto key = std::make_pair(g_device, N);
+  auto key = std::make_pair(tl_device, N);
   auto it = c.tab.find(key);
   if (it == c.tab.end()) {
     std::vector<cplx<T>> h(N);
@@ -148,6 +279,7 @@ template int twiddles<float>(int, const cplx<float> **);
 template int twiddles<double>(int, const cplx<double> **);
 
 void wct_fast_release();  // wct_fast.cu: the radix-16 twiddle tables
+void pool_shutdown();      // multi.cu
 
 static void free_tables() {
   {
@@ -211,24 +343,37 @@ int wtb_device_count(void) {
 }
 
 int wtb_init(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  return bind_device(device);
+  WTB_TRY(check_device(device));
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_default_device = device;
+  }
+  // one process per GPU (torchrun): also make it the calling thread's current device
+  WTB_CUDA(cudaSetDevice(device));
+  return WTB_OK;
 }
 
 void wtb_shutdown(void) {
-  if (g_device < 0) return;
-  cudaDeviceSynchronize();
+  pool_shutdown();
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
   {
+    // the sets stay with their threads (they are reused if the thread calls again); their
+    // memory goes now.  release_set's cudaFree waits for the work that uses each block.
     std::lock_guard<std::mutex> lk(g_arena_mu);
-    for (Arena *a : g_arenas) {
-      if (a->ptr) cudaFree(a->ptr);
-      a->ptr = nullptr;
-      a->cap = 0;
-    }
+    for (ArenaSet *s : g_sets) release_set(s);
   }
   free_tables();
   wct_fast_release();
+  cudaSetDevice(cur);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_default_device = -1;
 }
+
+uint64_t wtb_scratch_bytes(void) { return (uint64_t)scratch_bytes_held(); }
 
 const char *wtb_last_error(void) { return g_err; }
 

@@ -234,12 +234,27 @@ template <typename T> static size_t pair_bytes(int n0, int N, int S) {
   return sizeof(cplx<T>) * 2 * (size_t)N + sizeof(vec4<T>) * (size_t)S * N;
 }
 
+static thread_local bool g_in_shard = false;   // set on a pool worker while it runs its block
+
 template <typename T>
 static int xwt_wct_entry(const void *y1, const void *y2, int64_t batch, int n0, int N, double dt,
                          double dj, const Axes &ax, double f0, int flags, void *wct_out,
                          void *phase_out, void *w12_out, cudaStream_t st) {
   const int S = ax.J + 1;
   const size_t plane = (size_t)S * n0;
+  // host buffers, several GPUs (wtb_init_multi): contiguous blocks of pairs, one per device
+  if (!(flags & WTB_DEVICE_PTRS) && pool_size() > 1 && batch >= 2 * pool_size() && !g_in_shard) {
+    return run_sharded_fn(batch, 2, st, [&](int, int64_t first, int64_t count, cudaStream_t s) {
+      g_in_shard = true;
+      g_force_generic = flags & WTB_GENERIC_ONLY;
+      const int rc = xwt_wct_entry<T>((const T *)y1 + first * n0, (const T *)y2 + first * n0, count, n0, N, dt, dj, ax,
+                                      f0, flags, wct_out ? (T *)wct_out + first * plane : nullptr,
+                                      phase_out ? (T *)phase_out + first * plane : nullptr,
+                                      w12_out ? (cplx<T> *)w12_out + first * plane : nullptr, s);
+      g_in_shard = false;
+      return rc;
+    });
+  }
   // stage inputs interleaved [pair, 2, n0] and outputs per chunk
   const size_t per_pair = sizeof(T) * (2 * (size_t)n0 + (wct_out ? plane : 0) + (phase_out ? plane : 0) +
                                        (w12_out ? 2 * plane : 0));
@@ -306,6 +321,56 @@ static void coi_ranges(int nsurr, double dt, const Axes &ax, double f0, std::vec
     }
     if (lo >= 0) { (*tlo)[s] = lo; (*thi)[s] = hi; (*any)[s] = 1; }
   }
+}
+
+// rows with at least one sample inside the reliable region (multi.cu's percentile step)
+void mc_row_has_points(int nsurr, double dt, const Axes &ax, double f0, std::vector<uint8_t> *any) {
+  std::vector<int> tlo, thi;
+  coi_ranges(nsurr, dt, ax, f0, &tlo, &thi, any);
+}
+
+// Percentile step on the device, one thread per scale row, the SAME double operations in the same
+// order as wtb_wct_sig_from_hist (runtime.cu) -- explicit _rn intrinsics so that no multiply-add
+// is contracted: bit-identical thresholds, and the whole Monte-Carlo step stays on one stream.
+__global__ void k_sig_from_hist(const unsigned long long *__restrict__ hist, int S, int maxscale, double level,
+                                const uint8_t *__restrict__ has_points, double *__restrict__ sig95) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int nb = WTB_NBINS;
+  if (s >= maxscale) {
+    sig95[s] = (has_points && has_points[s]) ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+    return;
+  }
+  const unsigned long long *h = hist + (size_t)s * nb;
+  unsigned long long tot_i = 0;
+  int b_first = -1, b_last = -1;
+  for (int b = 0; b < nb; ++b)
+    if (h[b]) { tot_i += h[b]; if (b_first < 0) b_first = b; b_last = b; }
+  if (b_first < 0) { sig95[s] = __longlong_as_double(0x7ff8000000000000LL); return; }
+  // the host loop accumulates the counts in double: sums of integers below 2^53 are exact
+  const double tot = (double)tot_i;
+  auto Pof = [&](double cum) { return __ddiv_rn(__dsub_rn(cum, 0.5), tot); };
+  auto Yof = [&](int b) { return __ddiv_rn(__dadd_rn((double)b, 0.5), (double)nb); };
+  const double P_front = Pof((double)h[b_first]), P_back = Pof(tot);
+  double v;
+  if (level <= P_front) v = Yof(b_first);
+  else if (level >= P_back) v = Yof(b_last);
+  else {
+    // interval [i-1, i] over the non-empty bins with P[i-1] <= level < P[i]
+    double cum = (double)h[b_first];
+    double p_prev = P_front, p_cur = P_front;
+    int y_prev = b_first, y_cur = b_first;
+    for (int b = b_first + 1; b <= b_last; ++b) {
+      if (!h[b]) continue;
+      cum = __dadd_rn(cum, (double)h[b]);
+      p_prev = p_cur; y_prev = y_cur;
+      p_cur = Pof(cum); y_cur = b;
+      if (p_cur > level) break;
+    }
+    const double slope = __ddiv_rn(__dsub_rn(Yof(y_cur), Yof(y_prev)), __dsub_rn(p_cur, p_prev));
+    v = __dadd_rn(__dmul_rn(slope, __dsub_rn(level, p_prev)), Yof(y_prev));
+  }
+  sig95[s] = v;
 }
 
 template <typename T>
@@ -375,7 +440,7 @@ extern "C" int wtb_xwt_wct(const void *y1, const void *y2, int64_t batch, int n0
   WTB_REQUIRE(wct_out || phase_out || w12_out, WTB_EINVAL, "wtb_xwt_wct: no output requested");
   WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
               "nfft=%d must be a power of two >= n0=%d", nfft, n0);
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, y1, stream);
   Axes ax;
   WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));
   if (batch == 0) return WTB_OK;
@@ -392,7 +457,7 @@ extern "C" int wtb_wct_mc_hist(double a1, double a2, double dt, double dj, doubl
   WTB_REQUIRE(hist && mc_count >= 0 && mc_first >= 0, WTB_EINVAL, "wtb_wct_mc_hist: bad arguments");
   WTB_REQUIRE(J >= 0, WTB_EINVAL, "wtb_wct_mc_hist needs a resolved J");
   WTB_REQUIRE(fabs(a1) < 1 && fabs(a2) < 1, WTB_EINVAL, "AR(1) coefficients must lie in (-1, 1)");
-  WTB_TRY(ensure_device());
+  WTB_ENTER(flags, hist, stream);
   int nsurr = 0, maxscale = 0;
   WTB_TRY(wtb_wct_mc_geometry(dt, dj, s0, J, f0, &nsurr, &maxscale));
   Axes ax;
@@ -405,4 +470,24 @@ extern "C" int wtb_wct_mc_hist(double a1, double a2, double dt, double dj, doubl
                                  surrogates, flags, hist, st);
   return mc_hist_entry<float>(a1, a2, dt, dj, ax, f0, nsurr, maxscale, mc_first, mc_count, seed,
                               surrogates, flags, hist, st);
+}
+
+// Device-resident percentile step: hist and sig95 are device buffers, has_points (may be NULL) is a
+// HOST array of S flags; everything is enqueued on `stream`.
+extern "C" int wtb_wct_sig_from_hist_device(const uint64_t *hist, int S, int maxscale, double level,
+                                            const uint8_t *row_has_points, double *sig95, void *stream) {
+  WTB_REQUIRE(hist && sig95 && S > 0 && S <= 4096, WTB_EINVAL, "wtb_wct_sig_from_hist_device: bad arguments");
+  WTB_REQUIRE(maxscale >= 0 && maxscale <= S, WTB_EINVAL, "maxscale out of range");
+  WTB_ENTER(WTB_DEVICE_PTRS, hist, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t *d_flags = nullptr;
+  if (row_has_points) {
+    void *prm = nullptr;
+    WTB_TRY(params_reserve(4096, &prm));
+    d_flags = (uint8_t *)prm;
+    WTB_CUDA(cudaMemcpyAsync(d_flags, row_has_points, S, cudaMemcpyHostToDevice, st));
+  }
+  k_sig_from_hist<<<(S + 63) / 64, 64, 0, st>>>((const unsigned long long *)hist, S, maxscale, level, d_flags, sig95);
+  WTB_LAUNCH_CHECK();
+  return WTB_OK;
 }

@@ -27,6 +27,8 @@
 
 namespace wtb {
 
+void coi_row_ranges(int n0, double dt, const Axes &ax, double f0, std::vector<ushort2> *out);   // cwt_fast.cu
+
 namespace {
 
 using fft16::br4;
@@ -207,10 +209,11 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
 // Plain CWT rows for nfft = 4096 (series of 2049..4096 samples): round 1 of kernel A on its own,
 // with the two FFMA2 lanes carrying TWO SERIES instead of the two members of a pair.
 // xhat: [batch, 4096]; outputs (either may be null): power / coef [batch, S, n0].
+// coi (may be null): per-row sample interval inside the cone of influence; power outside it is NaN.
 __global__ void __launch_bounds__(kThreads, 3)
 k_cwt_rows_4096(const float2 *__restrict__ xhat, int64_t batch, int n0, int S, const WRow *__restrict__ rows,
                 const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
-                float *__restrict__ power, float2 *__restrict__ coef) {
+                float *__restrict__ power, float2 *__restrict__ coef, const ushort2 *__restrict__ coi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *Bre = reinterpret_cast<float2 *>(smem_raw);
   float2 *Bim = Bre + kBuf;
@@ -242,6 +245,7 @@ k_cwt_rows_4096(const float2 *__restrict__ xhat, int64_t batch, int n0, int S, c
   __syncthreads();   // tw2s visible
   fft4096_inv2(R, I, rp.L1, Bre, Bim, tw2s, tw3, j);
   const int64_t o1 = (b0 * S + s) * (int64_t)n0, o2 = o1 + (int64_t)S * n0;
+  const int tlo = coi ? coi[s].x : 0, thi = coi ? coi[s].y : kN;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int t = j + 256 * r;
@@ -251,7 +255,8 @@ k_cwt_rows_4096(const float2 *__restrict__ xhat, int64_t batch, int n0, int S, c
         if (second) coef[o2 + t] = make_float2(R[r].y, I[r].y);
       }
       if (power) {
-        const float2 pw = fma2(R[r], R[r], mul2(I[r], I[r]));
+        float2 pw = fma2(R[r], R[r], mul2(I[r], I[r]));
+        if (t < tlo || t > thi) pw = make_float2(NAN, NAN);
         __stcs(power + o1 + t, pw.x);
         if (second) __stcs(power + o2 + t, pw.y);
       }
@@ -452,16 +457,15 @@ k_wct_coh_4096(const float4 *__restrict__ spec, int n0, int S, const WRow *__res
 struct Tables {
   float2 *tw2 = nullptr;   // [16][16]  exp(+2*pi*i*r*k/256)
   float2 *tw3 = nullptr;   // [16][256] exp(+2*pi*i*r*j/4096)
-  int device = -1;
 };
 std::mutex g_tab_mu;
-Tables g_tab;
+std::map<int, Tables> g_tab;   // per device (one process may drive several: wtb_init_multi)
 
 int ensure_tables(const float2 **tw2, const float2 **tw3) {
   std::lock_guard<std::mutex> lk(g_tab_mu);
-  int dev = 0;
-  WTB_CUDA(cudaGetDevice(&dev));
-  if (g_tab.device != dev) {
+  const int dev = current_device();
+  auto it = g_tab.find(dev);
+  if (it == g_tab.end()) {
     std::vector<float2> h2(256), h3(4096);
     const long double two_pi = 2.0L * 3.141592653589793238462643383279502884L;
     for (int r = 0; r < 16; ++r) {
@@ -474,17 +478,15 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
         h3[r * 256 + jj] = make_float2((float)cosl(ang), (float)sinl(ang));
       }
     }
-    float2 *d2 = nullptr, *d3 = nullptr;
-    WTB_CUDA(cudaMalloc(&d2, sizeof(float2) * 256));
-    WTB_CUDA(cudaMalloc(&d3, sizeof(float2) * 4096));
-    WTB_CUDA(cudaMemcpy(d2, h2.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
-    WTB_CUDA(cudaMemcpy(d3, h3.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice));
-    g_tab.tw2 = d2;   // kept until wtb_shutdown (34 KB)
-    g_tab.tw3 = d3;
-    g_tab.device = dev;
+    Tables t;
+    WTB_CUDA(cudaMalloc(&t.tw2, sizeof(float2) * 256));
+    WTB_CUDA(cudaMalloc(&t.tw3, sizeof(float2) * 4096));
+    WTB_CUDA(cudaMemcpy(t.tw2, h2.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
+    WTB_CUDA(cudaMemcpy(t.tw3, h3.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice));
+    it = g_tab.emplace(dev, t).first;   // kept until wtb_shutdown (34 KB)
   }
-  *tw2 = g_tab.tw2;
-  *tw3 = g_tab.tw3;
+  *tw2 = it->second.tw2;
+  *tw3 = it->second.tw3;
   return WTB_OK;
 }
 
@@ -493,9 +495,11 @@ int ensure_tables(const float2 **tw2, const float2 **tw3) {
 // wtb_shutdown: the radix-16 twiddle tables go with the arenas
 void wct_fast_release() {
   std::lock_guard<std::mutex> lk(g_tab_mu);
-  if (g_tab.tw2) cudaFree(g_tab.tw2);
-  if (g_tab.tw3) cudaFree(g_tab.tw3);
-  g_tab = Tables();
+  for (auto &kv : g_tab) {
+    if (kv.second.tw2) cudaFree(kv.second.tw2);
+    if (kv.second.tw3) cudaFree(kv.second.tw3);
+  }
+  g_tab.clear();
 }
 
 static void fill_rows(const Axes &ax, double dt, double f0, std::vector<WRow> *rows) {
@@ -525,22 +529,29 @@ static void fill_rows(const Axes &ax, double dt, double f0, std::vector<WRow> *r
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, float2 *d_coef, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (N != kN || f0 < kMinF0 || (flags & WTB_COI_MASK) || S > kMaxRowsC) return 1;
+  if (N != kN || f0 < kMinF0 || S > kMaxRowsC) return 1;
   std::vector<WRow> rows;
   fill_rows(ax, dt, f0, &rows);
   const float2 *tw2 = nullptr, *tw3 = nullptr;
   WTB_TRY(ensure_tables(&tw2, &tw3));
   // row parameters go to the per-thread parameter buffer (the caller's arena holds xhat)
   void *prm = nullptr;
-  WTB_TRY(params_reserve(sizeof(WRow) * kMaxRowsC, &prm));
+  WTB_TRY(params_reserve((sizeof(WRow) + sizeof(ushort2)) * kMaxRowsC, &prm));
   WRow *d_rows = (WRow *)prm;
   WTB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WRow) * S, cudaMemcpyHostToDevice, st));
+  ushort2 *d_coi = nullptr;
+  if ((flags & WTB_COI_MASK) && d_power) {
+    std::vector<ushort2> rng;
+    coi_row_ranges(n0, dt, ax, f0, &rng);
+    d_coi = (ushort2 *)(d_rows + kMaxRowsC);
+    WTB_CUDA(cudaMemcpyAsync(d_coi, rng.data(), sizeof(ushort2) * S, cudaMemcpyHostToDevice, st));
+  }
   const int64_t nrows = (batch + 1) / 2 * S;
   WTB_REQUIRE(nrows < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
   const size_t smem = 2 * sizeof(float2) * kBuf + sizeof(float2) * 256;
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_cwt_rows_4096<<<(unsigned)nrows, kThreads, smem, st>>>(d_xhat, batch, n0, S, d_rows, tw2, tw3, (float)f0, d_power,
-                                                          d_coef);
+                                                          d_coef, d_coi);
   WTB_LAUNCH_CHECK();
   return WTB_OK;
 }

@@ -36,11 +36,14 @@ def cwt_power_resident(x, power, dt, dj, s0, J, f0=6.0, generic_only=False):
     """Fused CWT+power of a device-resident batch.
 
     x: torch CUDA float32/float64 tensor [batch, n0]; power: preallocated
-    [batch, J+1, n0] tensor of the same dtype.  Enqueued on torch's current
-    stream; nothing is copied or synchronised."""
+    [batch, J+1, n0] tensor of the same dtype.  Runs on the device that owns x
+    (the library reads it off the pointer), enqueued on torch's current stream
+    of that device; nothing is copied or synchronised."""
     import torch
     if not (x.is_cuda and power.is_cuda and x.is_contiguous() and power.is_contiguous()):
         raise ValueError("x and power must be contiguous CUDA tensors")
+    if x.device != power.device:
+        raise ValueError("x and power must live on the same device")
     if x.dtype != power.dtype or x.dtype not in (torch.float32, torch.float64):
         raise ValueError("x and power must both be float32 or both float64")
     batch, n0 = x.shape
@@ -48,7 +51,7 @@ def cwt_power_resident(x, power, dt, dj, s0, J, f0=6.0, generic_only=False):
         raise ValueError(f"power must have shape {(batch, int(J) + 1, n0)}")
     _shim.cwt_power_device(x.data_ptr(), batch, n0, dt, dj, s0, int(J), f0, power.data_ptr(),
                            f64=x.dtype == torch.float64,
-                           stream=torch.cuda.current_stream().cuda_stream, generic_only=generic_only)
+                           stream=torch.cuda.current_stream(x.device).cuda_stream, generic_only=generic_only)
     return power
 
 
@@ -66,7 +69,7 @@ def cwt_batch_resident(x, dt, dj, s0, J, f0=6.0, detrend=True, remove_mean=False
         raise ValueError("x must be a contiguous CUDA float32/float64 tensor")
     batch, n0 = x.shape
     f64 = x.dtype == torch.float64
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream(x.device).cuda_stream
     y = torch.empty_like(x)
     ar1 = torch.empty(batch, dtype=torch.float64, device=x.device)
     _shim.series_prep_device(x.data_ptr(), batch, n0, y.data_ptr(), ar1.data_ptr(), detrend=detrend,
@@ -94,7 +97,7 @@ def wct_hist_resident(hist, a1, a2, dt, dj, s0, J, f0, mc_first, mc_count, seed,
     if tuple(hist.shape) != (int(J) + 1, _shim.NBINS):
         raise ValueError(f"hist must have shape {(int(J) + 1, _shim.NBINS)}")
     _shim.wct_mc_hist_device(a1, a2, dt, dj, s0, int(J), f0, mc_first, mc_count, seed, hist.data_ptr(),
-                             f64=f64, white=white, stream=torch.cuda.current_stream().cuda_stream)
+                             f64=f64, white=white, stream=torch.cuda.current_stream(hist.device).cuda_stream)
     return hist
 
 

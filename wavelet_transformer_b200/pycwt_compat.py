@@ -354,7 +354,7 @@ def pycwt_cache_file(al1, al2, dt, dj, s0, J, wavelet="morlet") -> Path:
 
 
 def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="morlet", mc_count=300,
-                     progress=True, cache=True, seed=0, white=False, surrogates=None, n_shards=1,
+                     progress=True, cache=True, seed=0, white=False, surrogates=None, n_gpus=None,
                      precision=None):
     """Monte Carlo coherence significance (one value per scale).
 
@@ -362,6 +362,10 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="
     coherence -> per-scale histograms.  ``cache=True`` stores the result on disk
     keyed on the exact arguments (pycwt keeps a similar cache under
     ~/.cache/pycwt).  ``surrogates`` ([mc_count, 2, N]) injects ready-made noise.
+
+    The realisations are spread over every GPU the library drives (``n_gpus`` here, or
+    ``_shim.init_multi`` / ``WTB_GPUS`` beforehand); the Philox streams are keyed by the global
+    realisation index, so the thresholds do not depend on the number of GPUs.
 
     ``precision``: "fp32" | "fp64" | None.  None keeps the global precision when surrogates
     are injected (the per-realisation parity mode) and uses the FP32 register-FFT kernels with
@@ -382,11 +386,10 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet="
                 return np.loadtxt(candidate, unpack=True)
             except OSError:
                 pass
-    _, maxscale = _shim.wct_mc_geometry(dt, dj, s0, J, wavelet.f0)
-    hist = _shim.wct_mc_hist(al1, al2, dt, dj, s0, J, wavelet.f0, mc_first=0, mc_count=mc_count,
-                             seed=seed, surrogates=surrogates, white=white, f64=f64)
-    has = _shim.row_has_points(dt, dj, s0, J, wavelet.f0)
-    sig95 = _shim.wct_sig_from_hist(hist, maxscale, significance_level, has)
+    if n_gpus is not None and int(n_gpus) != _shim.gpu_count():
+        _shim.init_multi(int(n_gpus))
+    sig95 = _shim.wct_significance(al1, al2, dt, dj, s0, J, wavelet.f0, level=significance_level,
+                                   mc_count=mc_count, seed=seed, surrogates=surrogates, white=white, f64=f64)
     if cache and surrogates is None:
         for target in [path] + ([pycwt_path] if pycwt_mode == "readwrite" else []):
             try:

@@ -218,8 +218,13 @@ def significance(signal, dt, scales, sigma_test=0, alpha=None,
         1 + alpha ** 2 - 2 * alpha * np.cos(2 * np.pi * freq))
     if sigma_test != 0:
         raise NotImplementedError("oracle covers sigma_test=0 only")
-    dofmin = wavelet.dofmin
-    signif = fft_theor * chi2_ppf_dof2(significance_level) / dofmin
+    dofmin = wavelet.dofmin          # 2 for the complex mothers, 1 for DOG (real)
+    if dofmin == 2:
+        chisquare = chi2_ppf_dof2(significance_level) / dofmin
+    else:
+        from scipy.stats import chi2
+        chisquare = chi2.ppf(significance_level, dofmin) / dofmin
+    signif = fft_theor * chisquare
     return signif, fft_theor
 
 
@@ -313,7 +318,12 @@ def xwt(y1, y2, dt, dj=1 / 12, s0=-1, J=-1, significance_level=0.95,
     Pk1 = ar1_spectrum(freq * dt, a1)
     Pk2 = ar1_spectrum(freq * dt, a2)
     dof = wavelet.dofmin
-    signif = std1 * std2 * (Pk1 * Pk2) ** 0.5 * chi2_ppf_dof2(significance_level) / dof
+    if dof == 2:
+        chisquare = chi2_ppf_dof2(significance_level) / dof
+    else:
+        from scipy.stats import chi2
+        chisquare = chi2.ppf(significance_level, dof) / dof
+    signif = std1 * std2 * (Pk1 * Pk2) ** 0.5 * chisquare
     return W12, coi, freq, signif
 
 

@@ -116,7 +116,7 @@ def test_cwt_coi_mask_fused_fast_kernels(shim, n0, batch):
     p, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=False)
     assert shim.kernel_launches() - launches == 2 * per_call          # same kernels with and without the mask
     g_mask, _ = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=False, coi_mask=True, generic_only=True)
-    _, _, freqs, coi = po.cwt(x[0], DT, 1 / 12, 2 * DT, -1)[1:5]
+    _, freqs, coi = po.cwt(x[0], DT, 1 / 12, 2 * DT, -1)[1:4]
     outside = (1 / freqs)[:, None] > coi[None, :]
     assert outside.any() and (~outside).any()
     for b in range(batch):
@@ -155,6 +155,39 @@ def test_cwt_other_mothers_fp64_and_fp32(shim, series, mother):
     p32, _ = shim.cwt(x, DT, 1 / 8, -1, -1, code, m, f64=False)
     ok, err = normwise_close(p32, np.abs(W_ref) ** 2, 1e-4)
     assert ok, err
+
+
+def test_other_mothers_significance_xwt_and_large_orders(shim, series):
+    """pycwt.significance and pycwt.xwt work for every mother (only flambda, dofmin,
+    gamma enter; xwt needs no smoothing), so run_cwt's non-Morlet branch must survive its default
+    calculate_significance=True; and z^m of a large-order Paul / DOG daughter must not overflow FP32."""
+    from src import cwt as cwt_mod
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    y = 100 * np.diff(np.log(series["cpi_value"]))
+    t = series["cpi_days"].astype("datetime64[D]")[1:]
+    alpha = po.ar1(y)[0]
+    for eng_m, ref_m in ((wavelet.Paul(4), po.Paul(4)), (wavelet.DOG(2), po.DOG(2)), (wavelet.MexicanHat(), po.DOG(2))):
+        data = cwt_mod.DataForCWT(t, y, eng_m, cwt_mod.DT, cwt_mod.DJ, cwt_mod.S0, cwt_mod.LEVELS)
+        res = cwt_mod.run_cwt(data)
+        W, sj, *_ = po.cwt(y, DT, 1 / 12, 2 * DT, 84.0, ref_m)
+        signif, _ = po.significance(1.0, DT, sj, 0, alpha, significance_level=0.95, wavelet=ref_m)
+        want = np.abs(W) ** 2 / signif[:, None]
+        assert np.abs(res.significance_levels - want).max() <= 1e-9 * want.max()
+    # xwt with a non-Morlet mother: W1 conj(W2) of the two transforms, red-noise significance from dofmin
+    a = series["pair_expectation"]          # (the merged inflation series makes pycwt.ar1 raise, as in the reference)
+    b = a[::-1].copy()
+    W12, coi, freq, signif = wavelet.xwt(a, b, DT, dj=1 / 8, s0=2 * DT, J=-1, wavelet=wavelet.Paul(4))
+    R12, rcoi, rfreq, rsig = po.xwt(a, b, DT, dj=1 / 8, s0=2 * DT, J=-1, wavelet=po.Paul(4))
+    assert np.abs(W12 - R12).max() <= 1e-10 * np.abs(R12).max()
+    assert np.allclose(signif, rsig, rtol=1e-12) and np.allclose(freq, rfreq, rtol=1e-13)
+    # large orders in FP32: finite everywhere and at the FP32 gate against the FP64 kernel
+    x = (a - a.mean()) / a.std()
+    for code, m in ((shim.PAUL, 20), (shim.DOG, 30)):
+        p32, _ = shim.cwt(x, DT, 1 / 8, -1, -1, code, m, f64=False)
+        p64, _ = shim.cwt(x, DT, 1 / 8, -1, -1, code, m, f64=True)
+        assert np.isfinite(p32).all() and np.isfinite(p64).all()
+        ok, err = normwise_close(p32, p64, 1e-4)
+        assert ok, (code, m, err)
 
 
 def test_icwt_and_mother_names(shim, series):

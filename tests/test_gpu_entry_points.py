@@ -184,8 +184,8 @@ def test_pycwt_facade_cwt_side_outputs(series):
     assert np.allclose(fft_, ffto) and np.allclose(fftfreqs, fqo)
     Wp = wavelet.cwt(x, DT, 1 / 12, 2 * DT, 40, wavelet="paul")[0]      # other mothers: tests/test_gpu_cwt.py
     assert np.abs(Wp - po.cwt(x, DT, 1 / 12, 2 * DT, 40, po.Paul(4))[0]).max() <= 1e-10 * np.abs(Wp).max()
-    with pytest.raises(NotImplementedError):
-        wavelet.xwt(x, x[::-1].copy(), DT, wavelet="paul")
+    with pytest.raises(NotImplementedError):                              # pycwt smooths with Morlet only
+        wavelet.wct(x, x[::-1].copy(), DT, sig=False, wavelet="paul")
 
 
 def test_series_prep_matches_reference_helpers(shim, series, helpers_golden):

@@ -82,6 +82,28 @@ def test_wavedec_cfg_lengths_and_haar_kat(shim, series):
     assert np.allclose(packed[:3] * np.sqrt(2), [3, 7, 11], atol=1e-14)
 
 
+def test_wavedec_pywt_documentation_examples(shim):
+    """The examples printed in the PyWavelets documentation (values in tests/test_oracle_pywt.py)
+    through wtb_wavedec / wtb_waverec and through the pywt façade: an anchor outside this repo for
+    the symmetric-extension and down-sampling phase of the GPU kernels (blocked and generic)."""
+    from test_oracle_pywt import PYWT_DOC_DWT, PYWT_DOC_WAVEDEC
+    from wavelet_transformer_b200 import pywt_compat as pywt
+    for x, name, cA, cD in PYWT_DOC_DWT:
+        lo, hi, rlo, rhi = _bank(name)
+        for generic in (False, True):
+            packed, lens = shim.wavedec(np.asarray(x, dtype=float), lo, hi, 1, f64=True, generic_only=generic)
+            assert list(lens) == [len(cA), len(cD)]
+            assert np.allclose(packed, np.concatenate([cA, cD]), atol=5e-9)
+            assert np.allclose(shim.waverec(packed, lens, rlo, rhi, f64=True, generic_only=generic), x, atol=1e-12)
+    x, name, level, want = PYWT_DOC_WAVEDEC
+    got = pywt.wavedec(np.asarray(x, dtype=float), name, level=level)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.allclose(g, w, atol=5e-9)
+    assert np.allclose(pywt.waverec(got, name), x, atol=1e-12)
+    assert pywt.dwt_max_level(1000, 10) == 6
+
+
 def test_wavedec_batch_fp32(shim):
     rng = np.random.default_rng(8)
     x = rng.standard_normal((100, 800))

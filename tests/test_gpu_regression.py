@@ -68,3 +68,12 @@ def test_time_scale_regression_modwt_and_approximation(series):
         _check(fit, ols_oracle.ols(b, ref_smooth[c]["signal"]), tol=1e-8)
     single = regression.simple_regression(a, b)
     _check(single, ols_oracle.ols(b, a))
+    # the reference's own form: simple_regression(data: DataFrame, x_var, y_var, add_constant)
+    import pandas as pd
+    df = pd.DataFrame({"infl": a, "expect": b})
+    named = regression.simple_regression(df, "infl", "expect")
+    _check(named, ols_oracle.ols(b, a))
+    assert named.param_names == ["const", "infl"]
+    no_const = regression.simple_regression(df, "infl", "expect", add_constant=False)
+    assert no_const.params.shape == (1,) and no_const.param_names == ["infl"]
+    assert no_const.params[0] == pytest.approx(float(a @ b / (a @ a)), rel=1e-10)

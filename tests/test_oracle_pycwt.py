@@ -135,3 +135,18 @@ def test_other_mothers_known_answers():
         rec = po.icwt(W, sj, 1.0, dj, mother)
         mid = slice(200, 824)
         assert np.abs(rec[mid] - x[mid]).std() < 0.1 * x.std()
+
+
+def test_published_chi_square_and_red_noise_values():
+    """Torrence & Compo (1998) sec. 4: the 95 % level of chi-square with two degrees of freedom is
+    5.99 (99 %: 9.21), and the normalised red-noise spectrum (their eq. 16) of alpha = 0.72 (their
+    Nino3 example) is (1 - a^2) / (1 + a^2 - 2 a cos(2 pi k / N))."""
+    assert po.chi2_ppf_dof2(0.95) == pytest.approx(5.991, abs=1e-3)
+    assert po.chi2_ppf_dof2(0.99) == pytest.approx(9.210, abs=1e-3)
+    a = 0.72
+    signif, theor = po.significance(1.0, 0.25, np.array([1.0, 4.0]), 0, a, significance_level=0.95)
+    period = np.array([1.0, 4.0]) * po.Morlet().flambda()
+    want = (1 - a * a) / (1 + a * a - 2 * a * np.cos(2 * np.pi * 0.25 / period))
+    assert np.allclose(theor, want, rtol=1e-14) and np.allclose(signif, want * 5.991464547107979 / 2, rtol=1e-12)
+    # zero lag-1 autocorrelation: white noise, flat spectrum of the signal's variance
+    assert np.allclose(po.significance(2.0, 0.25, np.array([1.0, 4.0]), 0, 0.0)[1], 2.0)

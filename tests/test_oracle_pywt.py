@@ -63,3 +63,41 @@ def test_symmetric_extension_longer_than_signal():
     x = np.arange(3.0)
     e = pw._sym_ext(x, 7)
     assert e.tolist() == [0, 0, 1, 2, 2, 1, 0, 0, 1, 2, 2, 1, 0, 0, 1, 2, 2]
+
+
+# ---- published known answers: the examples printed in the PyWavelets documentation ------------
+# (https://pywavelets.readthedocs.io: "Discrete Wavelet Transform (DWT)" and "Multilevel
+# decomposition using wavedec"; values as printed there, 8 decimals).  They pin the phase of the
+# symmetric extension and of the down-sampling (SURVEY App. B "medium confidence") from outside.
+PYWT_DOC_DWT = [
+    # (x, wavelet, cA, cD)
+    ([1, 2, 3, 4, 5, 6], "db1", [2.12132034, 4.94974747, 7.77817459], [-0.70710678, -0.70710678, -0.70710678]),
+    ([3, 7, 1, 1, -2, 5, 4, 6], "db2", [5.65685425, 7.39923721, 0.22414387, 3.33677403, 7.77817459],
+     [-2.44948974, -1.60368225, -4.44140056, -0.41361256, 1.22474487]),
+]
+PYWT_DOC_WAVEDEC = ([1, 2, 3, 4, 5, 6, 7, 8], "db1", 2,
+                    [[5.0, 13.0], [-2.0, -2.0], [-0.70710678, -0.70710678, -0.70710678, -0.70710678]])
+
+
+@pytest.mark.parametrize("x,name,cA,cD", PYWT_DOC_DWT)
+def test_pywt_documentation_dwt_examples(x, name, cA, cD):
+    a, d = pw.dwt(np.asarray(x, dtype=float), name)
+    assert np.allclose(a, cA, atol=5e-9) and np.allclose(d, cD, atol=5e-9)
+    assert np.allclose(pw.idwt(a, d, name), x, atol=1e-12)
+
+
+def test_pywt_documentation_wavedec_example():
+    x, name, level, want = PYWT_DOC_WAVEDEC
+    got = pw.wavedec(np.asarray(x, dtype=float), name, level=level)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.allclose(g, w, atol=5e-9)
+    assert np.allclose(pw.waverec(got, name), x, atol=1e-12)
+
+
+def test_pywt_documentation_max_level_and_db2_taps():
+    # "pywt.dwt_max_level(data_len=1000, filter_len=w.dec_len)" with w = Wavelet('sym5') prints 6
+    assert pw.dwt_max_level(1000, 10) == 6
+    # Wavelet('db2').dec_lo as printed in the documentation's filter-bank example
+    assert np.allclose(pw.Wavelet("db2").dec_lo, [-0.12940952255092145, 0.22414386804185735, 0.836516303737469,
+                                                  0.48296291314469025], atol=1e-9)

@@ -110,10 +110,29 @@ def _component_names(levels: int) -> List[str]:
     return [f"S_{levels}" if j == 0 else f"D_{levels - j + 1}" for j in range(levels + 1)]
 
 
-def simple_regression(x, y, add_constant: bool = True) -> ComponentFit:
-    """``sm.OLS(y, add_constant(x)).fit()`` for one pair of series (regression.py:54-64)."""
-    return fits_from_stats(_shim.rowwise_ols(np.asarray(x, dtype=float), np.asarray(y, dtype=float),
-                                             add_constant=add_constant, f64=True), add_constant)[0]
+def simple_regression(data, x_var, y_var=None, add_constant: bool = True) -> ComponentFit:
+    """``sm.OLS(data[y_var], add_constant(data[x_var])).fit()`` (src/regression.py:54-64).
+
+    The reference's form is ``simple_regression(data: DataFrame, x_var: str, y_var: str,
+    add_constant=True)``; anything indexable by column name (DataFrame, dict of arrays) works.
+    ``simple_regression(x, y)`` with two array-likes is kept as a shorthand.  The result is a
+    ``ComponentFit`` stand-in for statsmodels' results object (params, bse, tvalues, pvalues,
+    rsquared, rsquared_adj, nobs -- no ``.summary()``)."""
+    if isinstance(x_var, str):
+        if not isinstance(y_var, str):
+            raise TypeError("simple_regression(data, x_var, y_var): y_var must be a column name")
+        x, y, names = data[x_var], data[y_var], ["const", x_var]
+    else:
+        if isinstance(y_var, bool):          # simple_regression(x, y, False), the array shorthand
+            add_constant, y_var = y_var, None
+        if y_var is not None:
+            raise TypeError("simple_regression(x, y[, add_constant]) takes two arrays, or (data, x_var, y_var)")
+        x, y, names = data, x_var, None
+    fit = fits_from_stats(_shim.rowwise_ols(np.asarray(x, dtype=float), np.asarray(y, dtype=float),
+                                            add_constant=add_constant, f64=True), add_constant)[0]
+    if names:
+        fit.param_names = names if add_constant else names[1:]
+    return fit
 
 
 def _rowwise(xs: Sequence[npt.NDArray], ys: Sequence[npt.NDArray], add_constant: bool) -> List[ComponentFit]:

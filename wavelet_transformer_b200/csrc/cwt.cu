@@ -19,6 +19,9 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, float2 *d_coef, cudaStream_t st);
 
+// implemented in wct_fast.cu: forward FFTs with the radix-16 register kernel (FP32, N = 4096); 1 = not covered
+int fwd_fft_4096_try(const float *d_y, int64_t nseries, int n0, int N, float2 *d_xhat, cudaStream_t st);
+
 // One CTA = one (series, chunk of scales).  smem: 2 * N complex.
 template <typename T>
 __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
@@ -51,9 +54,13 @@ __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
       for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const int kk = (k < (N + 1) / 2) ? k : k - N;
         const T z = s_over_dt * (T(2.0 * kPi) * T(kk) / T(N));
-        T zm = T(1);
-        for (int i = 0; i < order; ++i) zm *= z;
-        const T g = mother == WTB_PAUL ? (z > T(0) ? zm * dev_exp<T>(-z) : T(0)) : zm * dev_exp<T>(T(-0.5) * z * z);
+        // z^m e^{-z} (Paul) and z^m e^{-z^2/2} (DOG) evaluated as one exponential: z^m alone
+        // overflows FP32 for large orders and scales while the product is tiny (inf * 0 = NaN)
+        const T az = fabs(z);
+        const T lz = T(order) * log(az);                      // -inf at z = 0: the daughter vanishes (m >= 1)
+        const T sgn = (z < T(0) && (order & 1)) ? T(-1) : T(1);
+        const T g = mother == WTB_PAUL ? (z > T(0) ? dev_exp<T>(lz - z) : T(0))
+                                       : (az > T(0) ? sgn * dev_exp<T>(lz - T(0.5) * z * z) : T(0));
         const T dr = nrm * pre_re * g, di = nrm * pre_im * g;
         cplx<T> v = xh[k];
         a[k] = mk<T>(v.x * dr - v.y * di, v.x * di + v.y * dr);
@@ -105,8 +112,16 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   const int threads = N >= 1024 ? 256 : (N >= 256 ? 128 : 64);
   WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
-  WTB_LAUNCH_CHECK();
+  int fwd_rc = 1;
+  if constexpr (sizeof(T) == 4) {
+    if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY))
+      fwd_rc = fwd_fft_4096_try((const float *)d_x, batch, n0, N, (float2 *)d_xhat, st);
+    if (fwd_rc < 0) return fwd_rc;
+  }
+  if (fwd_rc == 1) {
+    k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
+    WTB_LAUNCH_CHECK();
+  }
   if constexpr (sizeof(T) == 4) {
     if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef) {
       const int rc = cwt_fast_fold_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);

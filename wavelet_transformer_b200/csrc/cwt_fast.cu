@@ -361,19 +361,21 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 // and the L2 request rate becomes the limit.  It was dropped.
 constexpr int kMaxRowsF = 128;
 constexpr int kMinBatchF = 12;
+constexpr int kStageMinN0 = 1888;   // rows longer than this take the staged-store variant (see k_cwt_fast_fold)
 
-struct WarpSmemF {
+template <bool STAGE> struct WarpSmemF {
   float trr[32 * kTrStride];        // transpose buffer; its first 32 floats double as Y[k] of a single-pass row
   float tri[32 * kTrStride];
+  float2 stage[STAGE ? 16 : 1][32]; // STAGE: phase 0 of the current row, |w|^2 at t = 2u, (u, u + 512) per lane and p
 };
 
-template <int D> struct CtaSmemF {
+template <int D, bool STAGE> struct CtaSmemF {
   float4 tw_a[16][32];              // as in CtaSmem: twiddles of the 1024-point transform
   float4 tw_b[16][32];
   float4 tw_c[D - 1][16][32];       // exp(+2*pi*i*q*k/N) for the pair k = lane + 64 m, k + 32, q = 1 .. D-1
   RowParam row[kMaxRowsF];
   ushort2 coi[kMaxRowsF];           // COI only (see k_cwt_fast_1024)
-  WarpSmemF w[kWarpsDefault];
+  WarpSmemF<STAGE> w[kWarpsDefault];
 };
 
 // X^ is the only data a warp reads more than once: keep it in L1 ahead of everything else
@@ -387,18 +389,27 @@ __device__ __forceinline__ void st_stream(float *p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void st_stream2(float *p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
 __device__ __forceinline__ constexpr int below_pow2_16(int m) {
   return m < 8 ? below_pow2(m) : 8;
 }
 
-template <int D, bool COI>
+// STAGE: phase 0 waits in shared memory and whole (t, t + 1) pairs are stored -- DRAM traffic drops
+// from 1.14x to 0.99x of the algorithmic bytes and the re-reads disappear (ncu, profiles/), but
+// the staging costs 32 shared-memory instructions per row and 64 KB of L1 (the X^ re-reads then
+// miss it), so it only pays for long rows (n0 > kStageMinN0: measured 6.2 ms flat per 20 000
+// series against 3.3 ms + 1.6 ms * n0 / 1024 without it).
+template <int D, bool COI, bool STAGE>
 __global__ void __launch_bounds__(kWarpsDefault * 32, 1)
 k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
                 const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
                 float *__restrict__ power, int split) {
   constexpr int kNF = kN * D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CtaSmemF<D> &sm = *reinterpret_cast<CtaSmemF<D> *>(smem_raw);
+  CtaSmemF<D, STAGE> &sm = *reinterpret_cast<CtaSmemF<D, STAGE> *>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
@@ -422,7 +433,7 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     if (COI) sm.coi[i] = coi[i];
   }
   __syncthreads();
-  WarpSmemF &ws = sm.w[warp];
+  WarpSmemF<STAGE> &ws = sm.w[warp];
   float *const yr = ws.trr, *const yi = ws.tri;      // single-pass rows never touch the transpose buffer
   // consecutive series go to different SMs: a small batch spreads over the machine
   const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
@@ -436,7 +447,6 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     const int64_t b = it / split;
     const int c = (int)(it - b * split);
     const float2 *xh = xhat + b * kNF + lane;
-    float *out = power + b * (int64_t)S * n0 + D * lane;
 #pragma unroll 1
     for (int sq = D * c; sq < D * S; sq = (sq % D == D - 1) ? sq + D * (split - 1) + 1 : sq + 1) {
       const int s = sq / D, q = sq % D;
@@ -514,21 +524,62 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         __syncwarp();
         fft32::dit32(R, I, 5);
       }
-      // position p holds u = lane + 32 p (.x) and u + 512 (.y); this phase is sample t = D u + q.
-      // Default store policy: the other parts of the line follow within this row.
-      float *orow = out + (int64_t)s * n0 + q;
-      const int tl = D * lane + q;
+      // position p holds u = lane + 32 p (.x) and u + 512 (.y); this phase is sample t = 2 u + q.
+      // Phase 0 waits in shared memory (same lane writes and reads it: no synchronisation); phase 1
+      // pairs it with its own values, so a lane stores (t, t + 1) as one 8-byte word and a warp
+      // store covers 256 contiguous bytes -- whole 128-byte lines instead of every other float
+      // (stride-2 stores cost two L2 write requests per sector and partial-sector DRAM writes).
+      static_assert(D == 2, "the staged store pairs two phases");
       const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
+      const int u2 = 2 * lane;                        // t of phase 0 at p = 0
+      if (!STAGE) {
+        // each phase stores its own samples at stride 2; the halves of a line meet in L2
+        float *orow = power + (b * S + s) * (int64_t)n0 + u2 + q;
 #pragma unroll
-      for (int p = 0; p < 16; ++p) {
-        float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-        const int ta = tl + 32 * D * p, tb = ta + 512 * D;
-        if (COI) {
-          if (ta < tlo || ta > thi) pw.x = NAN;
-          if (tb < tlo || tb > thi) pw.y = NAN;
+        for (int p = 0; p < 16; ++p) {
+          float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+          const int ta = u2 + q + 64 * p, tb = ta + 1024;
+          if (COI) {
+            if (ta < tlo || ta > thi) pw.x = NAN;
+            if (tb < tlo || tb > thi) pw.y = NAN;
+          }
+          if (ta < n0) st_stream(orow + 64 * p, pw.x);
+          if (tb < n0) st_stream(orow + 64 * p + 1024, pw.y);
         }
-        if (ta < n0) st_stream(orow + 32 * D * p, pw.x);
-        if (tb < n0) st_stream(orow + 32 * D * p + 512 * D, pw.y);
+      } else if (q == 0) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+          if (COI) {
+            const int ta = u2 + 64 * p, tb = ta + 1024;
+            if (ta < tlo || ta > thi) pw.x = NAN;
+            if (tb < tlo || tb > thi) pw.y = NAN;
+          }
+          ws.stage[p][lane] = pw;
+        }
+      } else {
+        float *orow = power + (b * S + s) * (int64_t)n0 + u2;
+        const bool al8 = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);   // odd n0: every other row is only 4-byte aligned
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
+          const float2 p0 = ws.stage[p][lane];
+          const int ta = u2 + 64 * p, tb = ta + 1024;    // phase-0 samples; phase 1 is ta + 1, tb + 1
+          if (COI) {
+            if (ta + 1 < tlo || ta + 1 > thi) pw.x = NAN;
+            if (tb + 1 < tlo || tb + 1 > thi) pw.y = NAN;
+          }
+          if (al8 && ta + 1 < n0) st_stream2(orow + 64 * p, make_float2(p0.x, pw.x));
+          else {
+            if (ta < n0) st_stream(orow + 64 * p, p0.x);
+            if (ta + 1 < n0) st_stream(orow + 64 * p + 1, pw.x);
+          }
+          if (al8 && tb + 1 < n0) st_stream2(orow + 64 * p + 1024, make_float2(p0.y, pw.y));
+          else {
+            if (tb < n0) st_stream(orow + 64 * p + 1024, p0.y);
+            if (tb + 1 < n0) st_stream(orow + 64 * p + 1025, pw.y);
+          }
+        }
       }
     }
   }
@@ -680,14 +731,20 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   const int64_t machine_warps = (int64_t)sm_count() * kWarpsDefault;
   const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), machine_warps / batch));
   const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
-  const size_t smem = sizeof(CtaSmemF<2>);
-  auto run = [&](auto kern) -> int {
+  static_assert(sizeof(CtaSmemF<2, true>) <= 227 * 1024, "the fold kernel's tables, transpose buffers and staging rows must fit one CTA");
+  int stage_min = kStageMinN0;
+  if (const char *e = std::getenv("WTB_FOLD_STAGE_MIN")) stage_min = std::atoi(e);
+  const bool stage = n0 > stage_min;
+  auto run = [&](auto kern, size_t smem) -> int {
     WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   };
-  return coi ? run(k_cwt_fast_fold<2, true>) : run(k_cwt_fast_fold<2, false>);
+  if (stage) return coi ? run(k_cwt_fast_fold<2, true, true>, sizeof(CtaSmemF<2, true>))
+                        : run(k_cwt_fast_fold<2, false, true>, sizeof(CtaSmemF<2, true>));
+  return coi ? run(k_cwt_fast_fold<2, true, false>, sizeof(CtaSmemF<2, false>))
+             : run(k_cwt_fast_fold<2, false, false>, sizeof(CtaSmemF<2, false>));
 }
 
 }  // namespace wtb

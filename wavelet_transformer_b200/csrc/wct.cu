@@ -26,6 +26,9 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
                  float *d_wct, float *d_phase, float2 *d_w12, unsigned long long *d_hist,
                  const int *d_tlo, const int *d_thi, int maxscale, cudaStream_t st);
 
+// wct_fast.cu: forward FFTs with the radix-16 register kernel (FP32, N = 4096); 1 = not covered
+int fwd_fft_4096_try(const float *d_y, int64_t nseries, int n0, int N, float2 *d_xhat, cudaStream_t st);
+
 template <typename T> struct vec4_of;
 template <> struct vec4_of<float> { using type = float4; };
 template <> struct vec4_of<double> { using type = double4; };
@@ -202,8 +205,15 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
   WTB_CUDA(cudaFuncSetAttribute(k_wct_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
   WTB_REQUIRE(pairs * S < (1LL << 31) && pairs * 2 < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
-  k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
-  WTB_LAUNCH_CHECK();
+  int fwd_rc = 1;
+  if constexpr (std::is_same<T, float>::value) {
+    if (!g_force_generic) fwd_rc = fwd_fft_4096_try((const float *)d_y, pairs * 2, n0, N, (float2 *)d_xhat, st);
+    if (fwd_rc < 0) return fwd_rc;
+  }
+  if (fwd_rc == 1) {
+    k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
+    WTB_LAUNCH_CHECK();
+  }
   int fast_rc = 1;
   if constexpr (std::is_same<T, float>::value) {
     if (!g_force_generic)

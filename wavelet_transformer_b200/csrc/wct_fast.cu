@@ -127,7 +127,7 @@ __device__ __forceinline__ void fft4096_inv2(float2 (&R)[16], float2 (&I)[16], i
 // Kernel A: rounds 1 and 2 of one (pair, scale) row, filtered spectra out.
 // spec: [rows = pairs*S][4096] float4 = (P^.re, C^.re, P^.im, C^.im) * filter.
 __global__ void __launch_bounds__(kThreads, 3)
-k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__restrict__ rows,
+k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, int S_run, const WRow *__restrict__ rows,
                 const float2 *__restrict__ tw2, const float2 *__restrict__ tw3, float f0,
                 float4 *__restrict__ spec, float *__restrict__ phase, float2 *__restrict__ w12,
                 int smooth) {
@@ -137,9 +137,10 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
   float2 *tw2s = Bim + kBuf;                                         // [256]
   const int j = threadIdx.x;
   tw2s[j] = tw2[j];
-  const int64_t row = blockIdx.x;
-  const int64_t pair = row / S;
-  const int s = (int)(row % S);
+  // rows 0 .. S_run-1 of every pair (the larger scales go to k_wct_spec_direct)
+  const int64_t pair = blockIdx.x / S_run;
+  const int s = (int)(blockIdx.x % S_run);
+  const int64_t row = pair * S + s;
   const WRow rp = rows[s];
   const float2 *x1 = xhat + (pair * 2) * (int64_t)kN;
   const float2 *x2 = x1 + kN;
@@ -203,6 +204,143 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, const WRow *__re
       const float g = ex2(fmaf(rp.gcoef, k2v, -12.0f));
       srow[bin] = make_float4(R[r].x * g, R[r].y * g, -I[r].x * g, -I[r].y * g);
     }
+  }
+}
+
+// Kernel A for the LARGE scales: the same filtered spectra without a single transform.
+// A large-scale daughter keeps only B = O(10.6 / a) bins of X^ (a = s/dt * 2 pi / N), so
+//   W(t) = sum_l W^[l] e^{+2 pi i l t / N}           with W^ = X^ * daughter on B bins,
+//   |W1(t)|^2 = sum_m A1[m] e^{2 pi i m t / N},      A1[m]  = sum_l W1^[l+m] conj(W1^[l])   (|m| < B),
+//   W1 conj(W2)(t) = sum_m A12[m] e^{2 pi i m t / N}, A12[m] = sum_l W1^[l+m] conj(W2^[l]),
+// and the transform of such a field cut off at t < n0 (pycwt truncates before it smooths) is
+//   FFT(f rect)[k] = sum_m A[m] Dn[k - m],            Dn[d] = sum_{t < n0} e^{-2 pi i d t / N}
+// -- needed only for the |k| <= kc bins the row's Gaussian keeps.  That is 2 B^2 + 6 B (2 kc + 1)
+// complex multiply-adds per row (kc ~ 0.54 B) against four 4096-point transforms: a few per cent
+// of the work for the largest scales, break-even near B = 90.  Output: exactly the spectra
+// k_wct_spec_4096 stores (same layout, same bins), so kernels C and B do not change.
+constexpr int kDirB = 96;                    // widest band (bins) a row may have to come here
+constexpr int kDirKc = 56;                   // largest kc of such a row (kc = 5.68 / a ~ 0.54 B)
+constexpr int kDirDn = kDirB + kDirKc;       // Dn is tabulated for |d| <= kDirDn
+constexpr int kDirThreads = 128;
+
+struct DRow {
+  int l0;    // first bin of the daughter's support
+  int B;     // number of bins
+};
+
+__global__ void __launch_bounds__(kDirThreads)
+k_wct_spec_direct(const float2 *__restrict__ xhat, int S, int s_first, const WRow *__restrict__ rows,
+                  const DRow *__restrict__ drows, const float2 *__restrict__ dn, float f0,
+                  float4 *__restrict__ spec) {
+  __shared__ float2 w1[kDirB], w2[kDirB];
+  __shared__ float2 a1[kDirB], a2[kDirB], a12[2 * kDirB];     // a12[m + B - 1], |m| < B
+  __shared__ float2 sdn[2 * kDirDn + 1];                      // sdn[d + dm], |d| <= dm = B - 1 + kc
+  __shared__ float2 out[3][2 * kDirKc + 1];
+  const int tid = threadIdx.x;
+  const int nrun = S - s_first;
+  const int64_t pair = blockIdx.x / nrun;
+  const int s = s_first + (int)(blockIdx.x % nrun);
+  const WRow rp = rows[s];
+  const int l0 = drows[s].l0, B = drows[s].B, kc = rp.kc;
+  const int dm = B - 1 + kc, K = 2 * kc + 1;
+  const float2 *x1 = xhat + (pair * 2) * (int64_t)kN + l0;
+  const float2 *x2 = x1 + kN;
+  for (int l = tid; l < B; l += kDirThreads) {
+    const float z = fmaf(rp.a, (float)(l0 + l), -f0);
+    const float dgt = ex2(fmaf(z * z, -0.72134752044f, rp.lognorm));
+    const float2 p = __ldg(&x1[l]), q = __ldg(&x2[l]);
+    w1[l] = make_float2(p.x * dgt, p.y * dgt);
+    w2[l] = make_float2(q.x * dgt, q.y * dgt);
+  }
+  for (int d = tid; d <= 2 * dm; d += kDirThreads) sdn[d] = __ldg(&dn[d - dm + kDirDn]);
+  __syncthreads();
+  // correlations of the band-limited spectra: 4 B - 1 outputs of at most B terms
+  for (int idx = tid; idx < 4 * B - 1; idx += kDirThreads) {
+    const float2 *u, *v;
+    int m;
+    if (idx < B) { u = w1; v = w1; m = idx; }
+    else if (idx < 2 * B) { u = w2; v = w2; m = idx - B; }
+    else { u = w1; v = w2; m = idx - 2 * B - (B - 1); }
+    const int lo = m < 0 ? -m : 0, hi = m < 0 ? B : B - m;      // l in [lo, hi): 0 <= l + m < B
+    float ar = 0.0f, ai = 0.0f;
+    for (int l = lo; l < hi; ++l) {
+      const float2 x = u[l + m], y = v[l];                       // x conj(y)
+      ar = fmaf(x.x, y.x, fmaf(x.y, y.y, ar));
+      ai = fmaf(x.y, y.x, fmaf(-x.x, y.y, ai));
+    }
+    if (idx < B) a1[m] = make_float2(ar, ai);
+    else if (idx < 2 * B) a2[m] = make_float2(ar, ai);
+    else a12[m + B - 1] = make_float2(ar, ai);
+  }
+  __syncthreads();
+  // the cut-off at t < n0: convolution with the Dirichlet kernel, only for the bins the filter keeps
+  for (int idx = tid; idx < 3 * K; idx += kDirThreads) {
+    const int f = idx / K, k = idx - f * K - kc;
+    const float2 *dk = sdn + dm + k;                             // dk[-m] = Dn[k - m]
+    float sr = 0.0f, si = 0.0f;
+    if (f < 2) {
+      // real field: A[-m] = conj(A[m])
+      const float2 *a = f == 0 ? a1 : a2;
+      const float2 d0 = dk[0];
+      sr = a[0].x * d0.x;                                        // A[0] is real
+      si = a[0].x * d0.y;
+      for (int m = 1; m < B; ++m) {
+        const float2 am = a[m], dn_ = dk[-m], dp = dk[m];
+        // am * dn_ + conj(am) * dp
+        sr = fmaf(am.x, dn_.x + dp.x, fmaf(-am.y, dn_.y - dp.y, sr));
+        si = fmaf(am.x, dn_.y + dp.y, fmaf(am.y, dn_.x - dp.x, si));
+      }
+    } else {
+      for (int m = -(B - 1); m < B; ++m) {
+        const float2 am = a12[m + B - 1], d = dk[-m];
+        sr = fmaf(am.x, d.x, fmaf(-am.y, d.y, sr));
+        si = fmaf(am.x, d.y, fmaf(am.y, d.x, si));
+      }
+    }
+    out[f][k + kc] = make_float2(sr, si);
+  }
+  __syncthreads();
+  float4 *srow = spec + (pair * S + s) * (int64_t)kN;
+  for (int kk = tid; kk < K; kk += kDirThreads) {
+    const int k = kk - kc;
+    const float2 p1 = out[0][kk], p2 = out[1][kk], c = out[2][kk];
+    // P = |W1|^2 + i |W2|^2 travels as one complex field; 1/s and the 1/N of the inverse ride in g
+    const float g = ex2(fmaf(rp.gcoef, (float)(k * k), -12.0f)) * rp.inv_s;
+    srow[k >= 0 ? k : kN + k] = make_float4((p1.x - p2.y) * g, c.x * g, (p1.y + p2.x) * g, c.y * g);
+  }
+}
+
+// Forward transforms for this pipeline: two real series of a pair (or two neighbouring series of a
+// batch) in the two FFMA2 lanes, through the same three radix-16 passes: for real y the inverse
+// code gives sum_t y[t] e^{+2 pi i k t / N} = conj(X^[k]).  y: [nseries, n0], xhat: [nseries, 4096].
+// (The generic shared-memory Stockham kernel spent 3.5 % of a Monte-Carlo step on these 2 of the
+// 398 transforms of a realisation.)
+__global__ void __launch_bounds__(kThreads, 3)
+k_fwd_fft_4096(const float *__restrict__ y, int64_t nseries, int n0, const float2 *__restrict__ tw2,
+               const float2 *__restrict__ tw3, float2 *__restrict__ xhat) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *Bre = reinterpret_cast<float2 *>(smem_raw);
+  float2 *Bim = Bre + kBuf;
+  float2 *tw2s = Bim + kBuf;
+  const int j = threadIdx.x;
+  tw2s[j] = tw2[j];
+  const int64_t b0 = 2 * (int64_t)blockIdx.x;
+  const bool second = b0 + 1 < nseries;
+  const float *y1 = y + b0 * n0, *y2 = second ? y1 + n0 : y1;
+  float2 R[16], I[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int t = j + 256 * r;
+    R[br4(r)] = t < n0 ? make_float2(__ldg(y1 + t), __ldg(y2 + t)) : make_float2(0.0f, 0.0f);
+    I[br4(r)] = make_float2(0.0f, 0.0f);
+  }
+  __syncthreads();   // tw2s visible
+  fft4096_inv2(R, I, 4, Bre, Bim, tw2s, tw3, j);
+  float2 *o1 = xhat + b0 * kN + j, *o2 = o1 + kN;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    o1[256 * r] = make_float2(R[r].x, -I[r].x);
+    if (second) o2[256 * r] = make_float2(R[r].y, -I[r].y);
   }
 }
 
@@ -524,6 +662,21 @@ static void fill_rows(const Axes &ax, double dt, double f0, std::vector<WRow> *r
   }
 }
 
+// Forward FFTs of [nseries, n0] real rows into xhat [nseries, 4096] with the radix-16 register
+// kernel (FP32, N = 4096 only).  Returns 1 when the shape is not covered.
+int fwd_fft_4096_try(const float *d_y, int64_t nseries, int n0, int N, float2 *d_xhat, cudaStream_t st) {
+  if (N != kN || n0 > kN || nseries < 1) return 1;
+  const float2 *tw2 = nullptr, *tw3 = nullptr;
+  WTB_TRY(ensure_tables(&tw2, &tw3));
+  const size_t smem = 2 * sizeof(float2) * kBuf + sizeof(float2) * 256;
+  const int64_t ctas = (nseries + 1) / 2;
+  WTB_REQUIRE(ctas < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+  WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_fwd_fft_4096<<<(unsigned)ctas, kThreads, smem, st>>>(d_y, nseries, n0, tw2, tw3, d_xhat);
+  WTB_LAUNCH_CHECK();
+  return WTB_OK;
+}
+
 // FP32 CWT rows for nfft = 4096 from forward spectra xhat [batch, 4096] (cwt.cu tries this
 // before its generic row kernel).  Returns 1 when the shape is not covered.
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
@@ -576,10 +729,54 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
   const int64_t nrows = pairs * S;
   WTB_REQUIRE(nrows < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
   float4 *spec = d_spec;
-  WTB_CUDA(cudaFuncSetAttribute(k_wct_spec_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-  k_wct_spec_4096<<<(unsigned)nrows, kThreads, smem_a, st>>>(d_xhat, n0, S, d_rows, tw2, tw3, (float)f0,
-                                                            spec, d_phase, d_w12, smooth ? 1 : 0);
-  WTB_LAUNCH_CHECK();
+  // Rows whose daughter keeps at most `bmax` bins (the largest scales) skip the transforms: their
+  // filtered spectra come from k_wct_spec_direct.  Bands shrink with scale, so they are the rows
+  // from s_split on.  Only when nothing in the time domain is asked for (phase, cross spectrum).
+  int s_split = S;
+  std::vector<DRow> drows(S);
+  if (smooth && !d_phase && !d_w12) {
+    int bmax = 72;      // measured break-even against the transform rows (WTB_MC_DIRECT_B overrides, 0 = off)
+    if (const char *e = std::getenv("WTB_MC_DIRECT_B")) bmax = std::min(std::atoi(e), kDirB);
+    for (int q = S - 1; q >= 0; --q) {
+      const double a = ax.scales[q] / dt * 2.0 * kPi / kN;
+      int lo = (int)std::ceil((f0 - 5.3) / a), hi = (int)std::floor((f0 + 5.3) / a);
+      lo = std::max(lo, 0);
+      hi = std::min(hi, kN / 2 - 1);
+      drows[q].l0 = lo;
+      drows[q].B = hi - lo + 1;
+      if (drows[q].B < 1 || drows[q].B > bmax || rows[q].kc > kDirKc || rows[q].kc >= kN / 2) break;
+      s_split = q;
+    }
+  }
+  if (s_split > 0) {
+    WTB_CUDA(cudaFuncSetAttribute(k_wct_spec_4096, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    k_wct_spec_4096<<<(unsigned)(pairs * s_split), kThreads, smem_a, st>>>(d_xhat, n0, S, s_split, d_rows, tw2, tw3,
+                                                                        (float)f0, spec, d_phase, d_w12, smooth ? 1 : 0);
+    WTB_LAUNCH_CHECK();
+  }
+  if (s_split < S) {
+    // Dn[d] = sum_{t < n0} exp(-2 pi i d t / N) = exp(-i pi d (n0 - 1) / N) sin(pi d n0 / N) / sin(pi d / N)
+    std::vector<float2> dn(2 * kDirDn + 1);
+    for (int d = -kDirDn; d <= kDirDn; ++d) {
+      double re = n0, im = 0.0;
+      if (d != 0) {
+        const double mag = std::sin(kPi * d * n0 / kN) / std::sin(kPi * d / kN), ph = -kPi * d * (n0 - 1.0) / kN;
+        re = mag * std::cos(ph);
+        im = mag * std::sin(ph);
+      }
+      dn[d + kDirDn] = make_float2((float)re, (float)im);
+    }
+    void *prm = nullptr;
+    const size_t b_dn = (sizeof(float2) * dn.size() + 255) / 256 * 256;
+    WTB_TRY(params_reserve(b_dn + sizeof(DRow) * kMaxRowsC, &prm));
+    float2 *d_dn = (float2 *)prm;
+    DRow *d_drows = (DRow *)((char *)prm + b_dn);
+    WTB_CUDA(cudaMemcpyAsync(d_dn, dn.data(), sizeof(float2) * dn.size(), cudaMemcpyHostToDevice, st));
+    WTB_CUDA(cudaMemcpyAsync(d_drows, drows.data(), sizeof(DRow) * S, cudaMemcpyHostToDevice, st));
+    k_wct_spec_direct<<<(unsigned)(pairs * (S - s_split)), kDirThreads, 0, st>>>(d_xhat, S, s_split, d_rows, d_drows,
+                                                                                d_dn, (float)f0, spec);
+    WTB_LAUNCH_CHECK();
+  }
   if (!smooth) return WTB_OK;
   CohWin cw;
   cw.K = win.K;

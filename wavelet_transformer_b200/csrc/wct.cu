@@ -322,14 +322,28 @@ static void coi_ranges(int nsurr, double dt, const Axes &ax, double f0, std::vec
   tlo->assign(S, 1);
   thi->assign(S, 0);
   any->assign(S, 0);
+  // pycwt's predicate, period <= coi[t], with coi[t] = c (N/2 - |t - (N-1)/2|) in the same double
+  // operations.  |t - (N-1)/2| and N/2 - that are exact, and multiplying by c > 0 is monotone,
+  // so the predicate is monotone on either side of the centre: two binary searches per scale
+  // give the same interval a scan over t would (a scan costs S x N evaluations per call --
+  // 0.3 ms at the cfg5 shape, comparable to a 300-realisation run).
+  auto coi_at = [&](int t) { return c * (nsurr / 2.0 - std::fabs(t - (nsurr - 1) / 2.0)); };
+  const int mid_lo = (nsurr - 1) / 2, mid_hi = nsurr / 2;   // the one or two samples next to the centre
   for (int s = 0; s < S; ++s) {
     const double period = 1.0 / ax.freqs[s];
-    int lo = -1, hi = -2;
-    for (int t = 0; t < nsurr; ++t) {
-      const double coi = c * (nsurr / 2.0 - std::fabs(t - (nsurr - 1) / 2.0));
-      if (period <= coi) { if (lo < 0) lo = t; hi = t; }
+    if (!(period <= coi_at(mid_lo)) && !(period <= coi_at(mid_hi))) continue;
+    int a = 0, b = mid_lo;                   // first t in [0, mid_lo] inside (mid_lo is: coi is symmetric)
+    while (a < b) {
+      const int m = (a + b) / 2;
+      if (period <= coi_at(m)) b = m; else a = m + 1;
     }
-    if (lo >= 0) { (*tlo)[s] = lo; (*thi)[s] = hi; (*any)[s] = 1; }
+    int lo = a;
+    a = mid_hi; b = nsurr - 1;               // last t in [mid_hi, N-1] inside
+    while (a < b) {
+      const int m = (a + b + 1) / 2;
+      if (period <= coi_at(m)) a = m; else b = m - 1;
+    }
+    (*tlo)[s] = lo; (*thi)[s] = a; (*any)[s] = 1;
   }
 }
 

@@ -107,6 +107,23 @@ def main():
         except Exception as exc:  # a signature drift would show here rather than abort the listing
             out.append({"config": "entry point: " + name, "error": repr(exc)})
     shutil.rmtree(cache, ignore_errors=True)
+    # One call, every GPU of the box: pycwt_compat.wct_significance (what run_wct reaches) with the
+    # BASELINE cfg5 count, the library's own worker pool spreading the realisations (wtb_init_multi).
+    if "--mc-scaling" in sys.argv:
+        _shim.set_precision("fp32")
+        ref = None
+        n = 1
+        while n <= _shim.device_count():
+            wavelet.wct_significance(a1, a2, DT, 1 / 8, 2 * DT, 65, mc_count=2000, cache=False, n_gpus=n)   # pool + scratch warm-up
+            t_gpu = best_of(lambda: wavelet.wct_significance(a1, a2, DT, 1 / 8, 2 * DT, 65, mc_count=100_000, cache=False,
+                                                             seed=2024, n_gpus=n), 3)
+            sig = wavelet.wct_significance(a1, a2, DT, 1 / 8, 2 * DT, 65, mc_count=100_000, cache=False, seed=2024, n_gpus=n)
+            ref = sig if ref is None else ref
+            out.append({"config": f"one call: wct_significance mc_count=100000 on {n} GPU(s)", "precision": "fp32",
+                        "gpu_ms": 1e3 * t_gpu, "surrogates_per_s_gpu": 100_000 / t_gpu,
+                        "same_thresholds_as_one_gpu": bool(np.array_equal(sig, ref, equal_nan=True))})
+            n *= 2
+        _shim.init_multi(1)
     for line in out:
         print(json.dumps(line))
 

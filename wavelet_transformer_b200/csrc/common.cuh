@@ -44,6 +44,20 @@ void note_launch();
     }                                  \
   } while (0)
 
+// WTB_TRACE=1: host wall-clock per phase of a call, each closed with a stream synchronisation
+// (stderr).  A debugging aid for latency work; it serialises the call, never time with it on.
+struct TracePoint {
+  static bool on() {
+    static const bool v = std::getenv("WTB_TRACE") && std::atoi(std::getenv("WTB_TRACE"));
+    return v;
+  }
+  static void mark(cudaStream_t st, const char *label);
+};
+#define WTB_TRACE_POINT(st, label)                          \
+  do {                                                      \
+    if (::wtb::TracePoint::on()) ::wtb::TracePoint::mark((st), (label)); \
+  } while (0)
+
 #define WTB_TRY(expr)          \
   do {                         \
     int rc__ = (expr);         \
@@ -115,6 +129,14 @@ int staging_reserve(size_t bytes, void **out);
 // small buffer for kernel parameter tables, separate from the two arenas above so a callee can
 // fill it while its caller's arena holds live data
 int params_reserve(size_t bytes, void **out);
+// small page-locked host buffer of the calling thread (results that go back to pageable caller
+// memory bounce through it); grow-only, freed when the thread exits
+int pinned_reserve(size_t bytes, void **out);
+// Device -> caller's host buffer.  Results up to 4 MiB (every single-series request of the
+// reference) go through the thread's pinned buffer and a memcpy -- the call returns with the
+// data in place; larger ones are one cudaMemcpyAsync straight into the caller's memory, which
+// the caller's stream synchronisation completes.
+int copy_to_host(void *dst, const void *d_src, size_t bytes, cudaStream_t st);
 // bytes of device scratch the library holds right now, over all threads (leak tests)
 size_t scratch_bytes_held();
 

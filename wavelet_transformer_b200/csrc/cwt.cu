@@ -188,11 +188,9 @@ static int cwt_entry(const void *x, int64_t batch, int n0, int N, double dt, con
     WTB_CUDA(cudaMemcpyAsync(d_x, (const T *)x + b0 * n0, sizeof(T) * nb * n0, cudaMemcpyHostToDevice, st));
     WTB_TRY(cwt_device<T>(d_x, nb, n0, N, dt, ax, f0, flags, d_power, d_coef, st));
     if (power_out)
-      WTB_CUDA(cudaMemcpyAsync((T *)power_out + b0 * S * n0, d_power, sizeof(T) * nb * S * n0,
-                               cudaMemcpyDeviceToHost, st));
+      WTB_TRY(copy_to_host((T *)power_out + b0 * S * n0, d_power, sizeof(T) * nb * S * n0, st));
     if (coef_out)
-      WTB_CUDA(cudaMemcpyAsync((cplx<T> *)coef_out + b0 * S * n0, d_coef,
-                               sizeof(cplx<T>) * nb * S * n0, cudaMemcpyDeviceToHost, st));
+      WTB_TRY(copy_to_host((cplx<T> *)coef_out + b0 * S * n0, d_coef, sizeof(cplx<T>) * nb * S * n0, st));
     WTB_CUDA(cudaStreamSynchronize(st));
   }
   return WTB_OK;
@@ -267,7 +265,7 @@ static int icwt_impl(const void *coef, int64_t batch, int S, int n0, const doubl
     k_icwt<T><<<dim3((n0 + 255) / 256, (unsigned)nb), 256, 0, st>>>(d_in, S, n0, d_scales, factor, d_out);
     WTB_LAUNCH_CHECK();
     if (!dev) {
-      WTB_CUDA(cudaMemcpyAsync((char *)out + b0 * out_row, d_out, out_row * nb, cudaMemcpyDeviceToHost, st));
+      WTB_TRY(copy_to_host((char *)out + b0 * out_row, d_out, out_row * nb, st));
       WTB_CUDA(cudaStreamSynchronize(st));
     }
   }

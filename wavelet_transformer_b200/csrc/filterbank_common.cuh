@@ -128,7 +128,7 @@ static int run_batched(const void *in, void *out, int64_t batch, size_t in_row, 
     const int64_t nb = std::min(rows, batch - b0);
     WTB_CUDA(cudaMemcpyAsync(d_in, (const char *)in + b0 * in_row, in_row * nb, cudaMemcpyHostToDevice, st));
     WTB_TRY(launch(d_in, d_out, nb));
-    WTB_CUDA(cudaMemcpyAsync((char *)out + b0 * out_row, d_out, out_row * nb, cudaMemcpyDeviceToHost, st));
+    WTB_TRY(copy_to_host((char *)out + b0 * out_row, d_out, out_row * nb, st));
     WTB_CUDA(cudaStreamSynchronize(st));
   }
   return WTB_OK;

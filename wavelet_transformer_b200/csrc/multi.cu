@@ -327,7 +327,7 @@ extern "C" int wtb_wct_significance(double a1, double a2, double dt, double dj, 
       submit(w0, [=]() -> int {
         k_hist_reduce_peers<<<(unsigned)((cells + 255) / 256), 256, 0, w0->stream>>>(w0->d_hist, peers, G - 1, (int)cells);
         WTB_LAUNCH_CHECK();
-        WTB_CUDA(cudaMemcpyAsync(h, w0->d_hist, sizeof(uint64_t) * cells, cudaMemcpyDeviceToHost, w0->stream));
+        WTB_TRY(copy_to_host(h, w0->d_hist, sizeof(uint64_t) * cells, w0->stream));
         return WTB_OK;
       });
       WTB_TRY(wait(w0) == WTB_OK ? WTB_OK : (set_error("GPU 0: %s", w0->err), w0->rc));
@@ -337,7 +337,7 @@ extern "C" int wtb_wct_significance(double a1, double a2, double dt, double dj, 
         Worker *w = p->w[r].get();
         uint64_t *t = tmp.data();
         submit(w, [=]() -> int {
-          WTB_CUDA(cudaMemcpyAsync(t, w->d_hist, sizeof(uint64_t) * cells, cudaMemcpyDeviceToHost, w->stream));
+          WTB_TRY(copy_to_host(t, w->d_hist, sizeof(uint64_t) * cells, w->stream));
           return WTB_OK;
         });
         WTB_TRY(wait(w) == WTB_OK ? WTB_OK : (set_error("GPU %d: %s", w->device, w->err), w->rc));

@@ -132,7 +132,7 @@ extern "C" int wtb_rednoise(double a1, double a2, int nsurr, int64_t first, int6
   if (f64) WTB_TRY(rednoise_device<double>(a1, a2, nsurr, first, count, seed, flags & WTB_NOISE_WHITE, (double *)d, st));
   else WTB_TRY(rednoise_device<float>(a1, a2, nsurr, first, count, seed, flags & WTB_NOISE_WHITE, (float *)d, st));
   if (!(flags & WTB_DEVICE_PTRS)) {
-    WTB_CUDA(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st));
+    WTB_TRY(copy_to_host(out, d, bytes, st));
     WTB_CUDA(cudaStreamSynchronize(st));
   }
   return WTB_OK;

@@ -86,8 +86,8 @@ static int ratio_impl(const void *plane, int64_t batch, int S, int n0, const dou
     else k_ratio_planes<T, false><<<grid, 256, 0, st>>>(in, rows, S, n0, sg, sig_rows > 1, pw, rt);
     WTB_LAUNCH_CHECK();
     if (!dev) {
-      if (power_out) WTB_CUDA(cudaMemcpyAsync((char *)power_out + b0 * out_row, d_pow, out_row * nb, cudaMemcpyDeviceToHost, st));
-      if (ratio_out) WTB_CUDA(cudaMemcpyAsync((char *)ratio_out + b0 * out_row, d_rat, out_row * nb, cudaMemcpyDeviceToHost, st));
+      if (power_out) WTB_TRY(copy_to_host((char *)power_out + b0 * out_row, d_pow, out_row * nb, st));
+      if (ratio_out) WTB_TRY(copy_to_host((char *)ratio_out + b0 * out_row, d_rat, out_row * nb, st));
       WTB_CUDA(cudaStreamSynchronize(st));
     }
   }
@@ -118,8 +118,8 @@ static int arrows_impl(const void *phase, int64_t count, int flags, void *u_out,
     k_phase_arrows<T><<<blocks, 256, 0, st>>>(in, n, pu, pv);
     WTB_LAUNCH_CHECK();
     if (!dev) {
-      if (u_out) WTB_CUDA(cudaMemcpyAsync((T *)u_out + i0, d_u, sizeof(T) * n, cudaMemcpyDeviceToHost, st));
-      if (v_out) WTB_CUDA(cudaMemcpyAsync((T *)v_out + i0, d_v, sizeof(T) * n, cudaMemcpyDeviceToHost, st));
+      if (u_out) WTB_TRY(copy_to_host((T *)u_out + i0, d_u, sizeof(T) * n, st));
+      if (v_out) WTB_TRY(copy_to_host((T *)v_out + i0, d_v, sizeof(T) * n, st));
       WTB_CUDA(cudaStreamSynchronize(st));
     }
   }

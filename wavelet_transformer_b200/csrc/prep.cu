@@ -95,8 +95,8 @@ static int prep_impl(const void *x, int64_t batch, int n, int mode, int flags, v
   k_series_prep<T><<<(unsigned)blocks, warps * 32, 0, st>>>(d_x, batch, n, mode, d_y, d_ar1);
   WTB_LAUNCH_CHECK();
   if (!dev) {
-    if (y) WTB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(T) * (size_t)batch * n, cudaMemcpyDeviceToHost, st));
-    if (ar1) WTB_CUDA(cudaMemcpyAsync(ar1, d_ar1, sizeof(double) * batch, cudaMemcpyDeviceToHost, st));
+    if (y) WTB_TRY(copy_to_host(y, d_y, sizeof(T) * (size_t)batch * n, st));
+    if (ar1) WTB_TRY(copy_to_host(ar1, d_ar1, sizeof(double) * batch, st));
     WTB_CUDA(cudaStreamSynchronize(st));
   }
   return WTB_OK;

@@ -81,7 +81,7 @@ static int ols_impl(const void *x, int64_t x_rows, const void *y, int64_t y_rows
                                                            add_constant, d_s);
   WTB_LAUNCH_CHECK();
   if (!dev) {
-    WTB_CUDA(cudaMemcpyAsync(stats, d_s, sizeof(double) * 8 * rows, cudaMemcpyDeviceToHost, st));
+    WTB_TRY(copy_to_host(stats, d_s, sizeof(double) * 8 * rows, st));
     WTB_CUDA(cudaStreamSynchronize(st));
   }
   return WTB_OK;

@@ -1,6 +1,7 @@
 // Runtime plumbing of libwavelet_sm100a.so: errors, device binding, scratch
 // arenas, twiddle tables, and the small host-side pieces of the C ABI.
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 
 #include "common.cuh"
@@ -19,6 +20,17 @@ void set_error(const char *fmt, ...) {
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   set_error("CUDA error %s (%d) at %s:%d: %s", cudaGetErrorName(e), (int)e, file, line, what);
   return WTB_ECUDA;
+}
+
+void TracePoint::mark(cudaStream_t st, const char *label) {
+  static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  const auto t_host = std::chrono::steady_clock::now();
+  cudaStreamSynchronize(st);
+  const auto t_dev = std::chrono::steady_clock::now();
+  fprintf(stderr, "[wtb trace] %-28s host +%8.1f us, device drained +%8.1f us\n", label,
+          std::chrono::duration<double, std::micro>(t_host - last).count(),
+          std::chrono::duration<double, std::micro>(t_dev - t_host).count());
+  last = std::chrono::steady_clock::now();
 }
 
 static std::atomic<uint64_t> g_launches{0};
@@ -236,6 +248,48 @@ static int reserve(int which, size_t bytes, void **out) {
     g_scratch_bytes.fetch_add(want, std::memory_order_relaxed);
   }
   *out = a.ptr;
+  return WTB_OK;
+}
+
+struct PinnedBuf {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() {
+    if (ptr) cudaFreeHost(ptr);
+    cudaGetLastError();
+  }
+};
+static thread_local PinnedBuf tl_pinned;
+
+int pinned_reserve(size_t bytes, void **out) {
+  if (tl_pinned.cap < bytes) {
+    if (tl_pinned.ptr) WTB_CUDA(cudaFreeHost(tl_pinned.ptr));
+    tl_pinned.ptr = nullptr;
+    tl_pinned.cap = 0;
+    const size_t want = (bytes + 4095) & ~size_t(4095);
+    WTB_CUDA(cudaHostAlloc(&tl_pinned.ptr, want, cudaHostAllocDefault));
+    tl_pinned.cap = want;
+  }
+  *out = tl_pinned.ptr;
+  return WTB_OK;
+}
+
+int copy_to_host(void *dst, const void *d_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return WTB_OK;
+  if (bytes <= (size_t(4) << 20)) {
+    cudaPointerAttributes attr;
+    const bool pageable = cudaPointerGetAttributes(&attr, dst) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pageable) {
+      void *pin = nullptr;
+      WTB_TRY(pinned_reserve(bytes, &pin));
+      WTB_CUDA(cudaMemcpyAsync(pin, d_src, bytes, cudaMemcpyDeviceToHost, st));
+      WTB_CUDA(cudaStreamSynchronize(st));
+      std::memcpy(dst, pin, bytes);
+      return WTB_OK;
+    }
+  }
+  WTB_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
   return WTB_OK;
 }
 

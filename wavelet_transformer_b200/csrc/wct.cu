@@ -205,6 +205,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
   WTB_CUDA(cudaFuncSetAttribute(k_wct_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
   WTB_REQUIRE(pairs * S < (1LL << 31) && pairs * 2 < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
+  WTB_TRACE_POINT(st, "wct: scratch + small copies");
   int fwd_rc = 1;
   if constexpr (std::is_same<T, float>::value) {
     if (!g_force_generic) fwd_rc = fwd_fft_4096_try((const float *)d_y, pairs * 2, n0, N, (float2 *)d_xhat, st);
@@ -214,6 +215,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
     k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
     WTB_LAUNCH_CHECK();
   }
+  WTB_TRACE_POINT(st, "wct: forward transforms");
   int fast_rc = 1;
   if constexpr (std::is_same<T, float>::value) {
     if (!g_force_generic)
@@ -283,7 +285,6 @@ static int xwt_wct_entry(const void *y1, const void *y2, int64_t batch, int n0, 
   if (phase_out) { d_phase = (T *)p; p += al(sizeof(T) * rows * plane); }
   if (w12_out) { d_w12 = (cplx<T> *)p; }
   const cudaMemcpyKind in_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  const cudaMemcpyKind out_kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   for (int64_t b0 = 0; b0 < batch; b0 += rows) {
     const int64_t nb = std::min(rows, batch - b0);
     // interleave y1/y2 rows: dst pitch 2*n0, src pitch n0
@@ -298,11 +299,11 @@ static int xwt_wct_entry(const void *y1, const void *y2, int64_t batch, int n0, 
                           nullptr, 0, st));
     if (!dev) {
       if (wct_out)
-        WTB_CUDA(cudaMemcpyAsync((T *)wct_out + b0 * plane, d_wct, sizeof(T) * nb * plane, out_kind, st));
+        WTB_TRY(copy_to_host((T *)wct_out + b0 * plane, d_wct, sizeof(T) * nb * plane, st));
       if (phase_out)
-        WTB_CUDA(cudaMemcpyAsync((T *)phase_out + b0 * plane, d_phase, sizeof(T) * nb * plane, out_kind, st));
+        WTB_TRY(copy_to_host((T *)phase_out + b0 * plane, d_phase, sizeof(T) * nb * plane, st));
       if (w12_out)
-        WTB_CUDA(cudaMemcpyAsync((cplx<T> *)w12_out + b0 * plane, d_w12, sizeof(cplx<T>) * nb * plane, out_kind, st));
+        WTB_TRY(copy_to_host((cplx<T> *)w12_out + b0 * plane, d_w12, sizeof(cplx<T>) * nb * plane, st));
       WTB_CUDA(cudaStreamSynchronize(st));
     }  // device buffers: chunks reuse the arena without a host sync (all work is ordered on `st`)
   }
@@ -405,7 +406,9 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
   const int N = 1 << ilog2(nsurr);
   std::vector<int> tlo, thi;
   std::vector<uint8_t> any;
+  WTB_TRACE_POINT(st, "mc: entry");
   coi_ranges(nsurr, dt, ax, f0, &tlo, &thi, &any);
+  WTB_TRACE_POINT(st, "mc: coi ranges");
   const bool dev = flags & WTB_DEVICE_PTRS;
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t per_pair = sizeof(T) * 2 * (size_t)nsurr + pair_bytes<T>(nsurr, N, S);
@@ -415,8 +418,11 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
   size_t budget = size_t(20) << 30;
   if (const char *e = std::getenv("WTB_MC_CHUNK_MB")) {
     budget = (size_t)std::max(1, std::atoi(e)) << 20;
-  } else {
-    size_t free_b = 0, total_b = 0;  // never ask for more than half of what is free right now
+  } else if (per_pair * (size_t)mc_count > (size_t(4) << 30)) {
+    // never ask for more than half of what is free right now.  cudaMemGetInfo costs 1.6 - 8 ms of
+    // host time on this driver (WTB_TRACE), more than a whole 300-realisation run: only jobs
+    // that want more than 4 GiB of scratch pay for the question.
+    size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
       budget = std::max(size_t(3) << 29, std::min(budget, free_b / 2));
   }
@@ -430,6 +436,7 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
   unsigned long long *d_hist = (unsigned long long *)((char *)stage + al(sizeof(T) * rows * 2 * nsurr));
   unsigned long long *hist_dev = dev ? (unsigned long long *)hist : d_hist;
   if (!dev) WTB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * S * WTB_NBINS, st));
+  WTB_TRACE_POINT(st, "mc: budget, staging, memset");
   for (int64_t m0 = 0; m0 < mc_count; m0 += rows) {
     const int64_t nb = std::min(rows, mc_count - m0);
     const T *src = d_y;
@@ -440,15 +447,22 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
     } else {
       WTB_TRY(rednoise_device<T>(a1, a2, nsurr, mc_first + m0, nb, seed, flags & WTB_NOISE_WHITE, d_y, st));
     }
+    WTB_TRACE_POINT(st, "mc: surrogates");
     WTB_TRY(wct_device<T>(src, nb, nsurr, N, dt, dj, ax, f0, nullptr, nullptr, nullptr, hist_dev,
                           tlo.data(), thi.data(), maxscale, st));
     // chunks reuse the arena without a host sync: every kernel and copy is ordered on `st`
+    WTB_TRACE_POINT(st, "mc: pipeline (fft, A, C, B)");
   }
   if (!dev) {
-    std::vector<uint64_t> h((size_t)S * WTB_NBINS);
-    WTB_CUDA(cudaMemcpyAsync(h.data(), d_hist, sizeof(uint64_t) * h.size(), cudaMemcpyDeviceToHost, st));
+    // through a pinned bounce buffer: a pageable 528 KB copy costs 0.2 - 0.3 ms, this one 30 us
+    const size_t cells = (size_t)S * WTB_NBINS;
+    void *pin = nullptr;
+    WTB_TRY(pinned_reserve(sizeof(uint64_t) * cells, &pin));
+    const uint64_t *h = (const uint64_t *)pin;
+    WTB_CUDA(cudaMemcpyAsync(pin, d_hist, sizeof(uint64_t) * cells, cudaMemcpyDeviceToHost, st));
     WTB_CUDA(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < h.size(); ++i) hist[i] += h[i];
+    for (size_t i = 0; i < cells; ++i) hist[i] += h[i];
+    WTB_TRACE_POINT(st, "mc: histogram to host");
   }
   return WTB_OK;
 }

@@ -409,13 +409,16 @@ def bench_mc(c, args, sampler):
     traffic = _profile_json("r2_traffic_mc.json")
     roofline = {"bound": "fp32", "achieved": ach, "peak": FP32_PEAK_NOMINAL / 1e12, "unit": "TFLOP/s",
                 "frac": ach / (FP32_PEAK_NOMINAL / 1e12),
-                "traffic": (traffic or {}).get("dram_bytes_per_realisation_spec_kernel"),
-                "traffic_source": "profiles/r2_traffic_mc.json (ncu --set full, k_wct_spec_4096, per realisation)",
+                "traffic": ((traffic or {}).get("dram_bytes_per_realisation_pipeline") or 0) * R / c.world or None,
+                "traffic_source": "profiles/r2_traffic_mc.json: dram read+write bytes per realisation of the four "
+                                  "pipeline kernels (ncu --set full), times the realisations one GPU runs per step; "
+                                  "HBM is not the bound here (3.4 MB per realisation = 1.1 TB/s at this rate)",
                 "peak_source": "nominal non-tensor FP32 peak (148 SM x 128 lanes x 2 x 1.965 GHz); this path is "
                                "FP32-FLOP bound, tensor cores are not applicable (no dense contraction); "
                                "MEASURED_PEAKS.json has no FP32 entry",
-                "kernel": "the Monte-Carlo pipeline per GPU (k_wct_spec_4096 dominant, then k_wct_coh_4096, "
-                          "k_wct_boxcar_4096, k_fwd_fft, k_rednoise): profiles/ launch list gives the shares",
+                "kernel": "the Monte-Carlo pipeline per GPU: k_wct_spec_4096 46 %, k_wct_coh_4096 36 %, "
+                          "k_wct_boxcar_4096 11 %, k_wct_spec_direct 4 %, k_rednoise 1.5 %, k_fwd_fft_4096 0.8 % "
+                          "(profiles/r2_launches_mc.csv)",
                 "algorithmic_flop_per_realisation": MC_FLOP, "per_gpu": True,
                 "frac_at_measured_clock": (ach * 1e12 / (148 * 128 * 2 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6))}
     line = {

@@ -59,9 +59,10 @@ int  wtb_device_count(void);
 int  wtb_init(int device);
 /* One process, several GPUs (the reference's call sites are single-process: src/wct.py:106-118).
  * Starts one worker thread and stream per device 0 .. n_gpus-1 (n_gpus <= 0: WTB_GPUS, else all
- * visible devices).  From then on host-buffer calls of wtb_cwt / wtb_cwt_morlet / wtb_xwt_wct
- * split their batch into contiguous blocks, one per device, and wtb_wct_significance splits its
- * realisations; results do not depend on the number of devices.  WTB_DEVICE_PTRS calls are never
+ * visible devices).  From then on host-buffer calls of wtb_cwt / wtb_cwt_morlet / wtb_xwt_wct and
+ * of the filterbank entry points (wtb_modwt .. wtb_waverec) split their batch into contiguous
+ * blocks, one per device, and wtb_wct_significance splits its realisations; results do not
+ * depend on the number of devices.  WTB_DEVICE_PTRS calls are never
  * split.  wtb_gpu_count() is the number of devices in use (1 without a pool). */
 int  wtb_init_multi(int n_gpus);
 int  wtb_gpu_count(void);

@@ -96,6 +96,25 @@ def test_host_batches_are_split_over_the_pool(shim, pool, f64):
     assert np.array_equal(p1, p2) and np.array_equal(w1, w2) and np.array_equal(ph1, ph2)
 
 
+def test_host_filterbank_batches_are_split_over_the_pool(shim, pool):
+    """MODWT / inverse / MRA / DWT pair with host buffers: blocks of rows per device, same numbers."""
+    from wavelet_transformer_b200 import pywt_compat as pywt
+    w = pywt.Wavelet("sym4")
+    x = np.random.default_rng(21).standard_normal((9, 777))
+
+    def run():
+        m = shim.modwt(x, w.dec_lo, w.dec_hi, 5, f64=True)
+        packed, lens = shim.wavedec(x, w.dec_lo, w.dec_hi, 4, f64=True)
+        return (m, shim.imodwt(m, w.dec_lo, w.dec_hi, f64=True), shim.modwtmra_taps(m, w.dec_lo, w.dec_hi, f64=True),
+                packed, shim.waverec(packed, lens, w.rec_lo, w.rec_hi, f64=True))
+    two = run()
+    shim.init_multi(1)
+    one = run()
+    for a, b in zip(one, two):
+        assert np.array_equal(a, b)
+    assert np.abs(one[1] - x).max() < 1e-10
+
+
 def test_device_percentile_is_bit_identical(shim):
     import torch
     hist = shim.wct_mc_hist(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], mc_count=5, seed=1, f64=False)

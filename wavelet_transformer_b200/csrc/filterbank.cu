@@ -424,6 +424,18 @@ using namespace wtb;
 
 #define DISPATCH(fn, ...) ((flags & WTB_F64) ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
+// Host-buffer batches with several GPUs (wtb_init_multi): contiguous blocks of rows, one per device.
+// `call(in, out, count, stream)` runs the transform on `count` rows starting at the given pointers.
+template <typename F>
+static int shard_rows(const void *in, void *out, int64_t batch, size_t in_row, size_t out_row, int flags, void *stream,
+                      F call) {
+  if ((flags & WTB_DEVICE_PTRS) || pool_size() < 2 || batch < 2 * pool_size())
+    return call(in, out, batch, (cudaStream_t)stream);
+  return run_sharded_fn(batch, 2, (cudaStream_t)stream, [&](int, int64_t first, int64_t count, cudaStream_t s) {
+    return call((const char *)in + first * in_row, (char *)out + first * out_row, count, s);
+  });
+}
+
 extern "C" int wtb_modwt(const void *x, int64_t batch, int n, const double *g, const double *h, int L,
                          int J, int flags, void *w_out, void *stream) {
   WTB_REQUIRE(x && w_out && batch >= 0 && n > 0 && J >= 1 && J < 31, WTB_EINVAL, "wtb_modwt: bad arguments");
@@ -431,7 +443,9 @@ extern "C" int wtb_modwt(const void *x, int64_t batch, int n, const double *g, c
   WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
   WTB_ENTER(flags, x, stream);
   if (batch == 0) return WTB_OK;
-  return DISPATCH(modwt_impl, x, batch, n, taps, J, flags, w_out, (cudaStream_t)stream);
+  const size_t e = ((flags & WTB_F64) ? 8 : 4);
+  return shard_rows(x, w_out, batch, e * n, e * (size_t)(J + 1) * n, flags, stream,
+                    [&](const void *i, void *o, int64_t nb, cudaStream_t st) { return DISPATCH(modwt_impl, i, nb, n, taps, J, flags, o, st); });
 }
 
 extern "C" int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, const double *h, int L,
@@ -441,7 +455,9 @@ extern "C" int wtb_imodwt(const void *w, int64_t batch, int n, const double *g, 
   WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
   WTB_ENTER(flags, w, stream);
   if (batch == 0) return WTB_OK;
-  return DISPATCH(imodwt_impl, w, batch, n, taps, J, flags, x_out, (cudaStream_t)stream);
+  const size_t e = ((flags & WTB_F64) ? 8 : 4);
+  return shard_rows(w, x_out, batch, e * (size_t)(J + 1) * n, e * n, flags, stream,
+                    [&](const void *i, void *o, int64_t nb, cudaStream_t st) { return DISPATCH(imodwt_impl, i, nb, n, taps, J, flags, o, st); });
 }
 
 extern "C" int wtb_modwtmra(const void *w, int64_t batch, int n, const double *filt, int J, int flags,
@@ -449,7 +465,9 @@ extern "C" int wtb_modwtmra(const void *w, int64_t batch, int n, const double *f
   WTB_REQUIRE(w && out && filt && batch >= 0 && n > 0 && J >= 1, WTB_EINVAL, "wtb_modwtmra: bad arguments");
   WTB_ENTER(flags, w, stream);
   if (batch == 0) return WTB_OK;
-  return DISPATCH(mra_impl, w, batch, n, filt, J, flags, out, (cudaStream_t)stream);
+  const size_t e = ((flags & WTB_F64) ? 8 : 4);
+  return shard_rows(w, out, batch, e * (size_t)(J + 1) * n, e * (size_t)(J + 1) * n, flags, stream,
+                    [&](const void *i, void *o, int64_t nb, cudaStream_t st) { return DISPATCH(mra_impl, i, nb, n, filt, J, flags, o, st); });
 }
 
 extern "C" int wtb_modwtmra_taps(const void *w, int64_t batch, int n, const double *g, const double *h, int L,
@@ -459,7 +477,9 @@ extern "C" int wtb_modwtmra_taps(const void *w, int64_t batch, int n, const doub
   WTB_TRY(make_taps(g, h, L, 1.0 / std::sqrt(2.0), &taps));
   WTB_ENTER(flags, w, stream);
   if (batch == 0) return WTB_OK;
-  return DISPATCH(mra_taps_impl, w, batch, n, taps, g, h, J, flags, out, (cudaStream_t)stream);
+  const size_t e = ((flags & WTB_F64) ? 8 : 4);
+  return shard_rows(w, out, batch, e * (size_t)(J + 1) * n, e * (size_t)(J + 1) * n, flags, stream,
+                    [&](const void *i, void *o, int64_t nb, cudaStream_t st) { return DISPATCH(mra_taps_impl, i, nb, n, taps, g, h, J, flags, o, st); });
 }
 
 extern "C" int wtb_wavedec(const void *x, int64_t batch, int n, const double *dec_lo, const double *dec_hi,
@@ -469,7 +489,13 @@ extern "C" int wtb_wavedec(const void *x, int64_t batch, int n, const double *de
   WTB_TRY(make_taps(dec_lo, dec_hi, L, 1.0, &taps));
   WTB_ENTER(flags, x, stream);
   if (batch == 0) return WTB_OK;
-  return DISPATCH(wavedec_impl, x, batch, n, taps, level, flags, coeffs, (cudaStream_t)stream);
+  const size_t e = ((flags & WTB_F64) ? 8 : 4);
+  std::vector<int> lens(level + 1);
+  WTB_TRY(wtb_dwt_coeff_lens(n, L, level, lens.data()));
+  size_t total = 0;
+  for (int v : lens) total += (size_t)v;
+  return shard_rows(x, coeffs, batch, e * n, e * total, flags, stream,
+                    [&](const void *i, void *o, int64_t nb, cudaStream_t st) { return DISPATCH(wavedec_impl, i, nb, n, taps, level, flags, o, st); });
 }
 
 extern "C" int wtb_waverec(const void *coeffs, int64_t batch, const int *lens, int level, const double *rec_lo,
@@ -479,5 +505,11 @@ extern "C" int wtb_waverec(const void *coeffs, int64_t batch, const int *lens, i
   WTB_TRY(make_taps(rec_lo, rec_hi, L, 1.0, &taps));
   WTB_ENTER(flags, coeffs, stream);
   if (batch == 0) return WTB_OK;
-  return DISPATCH(waverec_impl, coeffs, batch, lens, level, taps, flags, x_out, (cudaStream_t)stream);
+  const size_t e = ((flags & WTB_F64) ? 8 : 4);
+  size_t total = 0;
+  for (int l = 0; l <= level; ++l) total += (size_t)lens[l];
+  const int nout = wtb_waverec_len(lens, level, L);
+  if (nout < 0) return nout;
+  return shard_rows(coeffs, x_out, batch, e * total, e * (size_t)nout, flags, stream,
+                    [&](const void *i, void *o, int64_t nb, cudaStream_t st) { return DISPATCH(waverec_impl, i, nb, lens, level, taps, flags, o, st); });
 }

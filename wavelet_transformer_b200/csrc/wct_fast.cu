@@ -218,93 +218,133 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, int S_run, const
 // complex multiply-adds per row (kc ~ 0.54 B) against four 4096-point transforms: a few per cent
 // of the work for the largest scales, break-even near B = 90.  Output: exactly the spectra
 // k_wct_spec_4096 stores (same layout, same bins), so kernels C and B do not change.
-constexpr int kDirB = 96;                    // widest band (bins) a row may have to come here
-constexpr int kDirKc = 56;                   // largest kc of such a row (kc = 5.68 / a ~ 0.54 B)
-constexpr int kDirDn = kDirB + kDirKc;       // Dn is tabulated for |d| <= kDirDn
+constexpr int kDirB = 128;                   // widest band (bins) a row may have to come here
+constexpr int kDirKc = 72;                   // largest kc of such a row (kc = 5.68 / a ~ 0.54 B)
+constexpr int kDirDn = kDirB + kDirKc + 2;   // Dn is tabulated for |d| <= kDirDn
 constexpr int kDirThreads = 128;
+constexpr int kDirKp = (kDirKc + 2) / 2;     // pairs (k, k + 1), k >= 0
+constexpr int kDirG = 8;                     // the sum over m is split over up to this many thread groups
 
 struct DRow {
   int l0;    // first bin of the daughter's support
   int B;     // number of bins
 };
 
+// Work per row: correlations 2 B^2 and the Dirichlet convolution 4.3 B^2 complex multiply-adds.
+// Both loops are arranged so that one thread owns several outputs that share their operands:
+//   step 2  thread m >= 0 forms A1[m], A2[m], A12[m] and A12[-m] from the same four loads
+//           (two of them warp-wide broadcasts): 4 loads per 4 multiply-adds;
+//   step 3  thread (k pair, m chunk) forms P1^, P2^, C^ at k, k + 1 and C^ at -k, -k - 1 (the real
+//           fields are Hermitian: P^[-k] = conj P^[k]) with two sliding windows over Dn: 5 loads
+//           (3 broadcasts) per 8 multiply-adds; the chunks' partial sums meet in shared memory
+//           and are added in a fixed order.
 __global__ void __launch_bounds__(kDirThreads)
 k_wct_spec_direct(const float2 *__restrict__ xhat, int S, int s_first, const WRow *__restrict__ rows,
                   const DRow *__restrict__ drows, const float2 *__restrict__ dn, float f0,
                   float4 *__restrict__ spec) {
-  __shared__ float2 w1[kDirB], w2[kDirB];
-  __shared__ float2 a1[kDirB], a2[kDirB], a12[2 * kDirB];     // a12[m + B - 1], |m| < B
-  __shared__ float2 sdn[2 * kDirDn + 1];                      // sdn[d + dm], |d| <= dm = B - 1 + kc
-  __shared__ float2 out[3][2 * kDirKc + 1];
+  __shared__ float2 u1[2 * kDirB], u2[2 * kDirB];             // W^[l] of the two series, zero for l >= B
+  __shared__ float2 a1[2 * kDirB], a2[2 * kDirB], a12[2 * kDirB];   // A[m] at index m + B - 1, |m| < B
+  __shared__ float2 sdn[2 * kDirDn + 1];                      // sdn[d + dm], |d| <= dm = B + kc + 1
+  __shared__ float2 part[kDirG][8][kDirKp];                   // partial sums of step 3
   const int tid = threadIdx.x;
   const int nrun = S - s_first;
   const int64_t pair = blockIdx.x / nrun;
   const int s = s_first + (int)(blockIdx.x % nrun);
   const WRow rp = rows[s];
   const int l0 = drows[s].l0, B = drows[s].B, kc = rp.kc;
-  const int dm = B - 1 + kc, K = 2 * kc + 1;
+  const int dm = B + kc + 1;
   const float2 *x1 = xhat + (pair * 2) * (int64_t)kN + l0;
   const float2 *x2 = x1 + kN;
-  for (int l = tid; l < B; l += kDirThreads) {
-    const float z = fmaf(rp.a, (float)(l0 + l), -f0);
-    const float dgt = ex2(fmaf(z * z, -0.72134752044f, rp.lognorm));
-    const float2 p = __ldg(&x1[l]), q = __ldg(&x2[l]);
-    w1[l] = make_float2(p.x * dgt, p.y * dgt);
-    w2[l] = make_float2(q.x * dgt, q.y * dgt);
+  for (int l = tid; l < 2 * B; l += kDirThreads) {
+    float2 p = make_float2(0.0f, 0.0f), q = p;
+    if (l < B) {
+      const float z = fmaf(rp.a, (float)(l0 + l), -f0);
+      const float dgt = ex2(fmaf(z * z, -0.72134752044f, rp.lognorm));
+      p = __ldg(&x1[l]);
+      q = __ldg(&x2[l]);
+      p = make_float2(p.x * dgt, p.y * dgt);
+      q = make_float2(q.x * dgt, q.y * dgt);
+    }
+    u1[l] = p;
+    u2[l] = q;
   }
   for (int d = tid; d <= 2 * dm; d += kDirThreads) sdn[d] = __ldg(&dn[d - dm + kDirDn]);
   __syncthreads();
-  // correlations of the band-limited spectra: 4 B - 1 outputs of at most B terms
-  for (int idx = tid; idx < 4 * B - 1; idx += kDirThreads) {
-    const float2 *u, *v;
-    int m;
-    if (idx < B) { u = w1; v = w1; m = idx; }
-    else if (idx < 2 * B) { u = w2; v = w2; m = idx - B; }
-    else { u = w1; v = w2; m = idx - 2 * B - (B - 1); }
-    const int lo = m < 0 ? -m : 0, hi = m < 0 ? B : B - m;      // l in [lo, hi): 0 <= l + m < B
-    float ar = 0.0f, ai = 0.0f;
-    for (int l = lo; l < hi; ++l) {
-      const float2 x = u[l + m], y = v[l];                       // x conj(y)
-      ar = fmaf(x.x, y.x, fmaf(x.y, y.y, ar));
-      ai = fmaf(x.y, y.x, fmaf(-x.x, y.y, ai));
+  // ---- step 2: correlations of the band-limited spectra
+  for (int m = tid; m < B; m += kDirThreads) {
+    float a1r = 0.0f, a1i = 0.0f, a2r = 0.0f, a2i = 0.0f, pr = 0.0f, pi = 0.0f, nr = 0.0f, ni = 0.0f;
+    for (int l = 0; l < B - m; ++l) {
+      const float2 xa = u1[l + m], xb = u2[l + m];             // per lane
+      const float2 ya = u1[l], yb = u2[l];                     // broadcast
+      a1r = fmaf(xa.x, ya.x, fmaf(xa.y, ya.y, a1r));           // xa conj(ya)
+      a1i = fmaf(xa.y, ya.x, fmaf(-xa.x, ya.y, a1i));
+      a2r = fmaf(xb.x, yb.x, fmaf(xb.y, yb.y, a2r));           // xb conj(yb)
+      a2i = fmaf(xb.y, yb.x, fmaf(-xb.x, yb.y, a2i));
+      pr = fmaf(xa.x, yb.x, fmaf(xa.y, yb.y, pr));             // A12[m]  += u1[l + m] conj(u2[l])
+      pi = fmaf(xa.y, yb.x, fmaf(-xa.x, yb.y, pi));
+      nr = fmaf(ya.x, xb.x, fmaf(ya.y, xb.y, nr));             // A12[-m] += u1[l] conj(u2[l + m])
+      ni = fmaf(ya.y, xb.x, fmaf(-ya.x, xb.y, ni));
     }
-    if (idx < B) a1[m] = make_float2(ar, ai);
-    else if (idx < 2 * B) a2[m] = make_float2(ar, ai);
-    else a12[m + B - 1] = make_float2(ar, ai);
+    a1[B - 1 + m] = make_float2(a1r, a1i);
+    a1[B - 1 - m] = make_float2(a1r, -a1i);                    // real field: A[-m] = conj A[m]
+    a2[B - 1 + m] = make_float2(a2r, a2i);
+    a2[B - 1 - m] = make_float2(a2r, -a2i);
+    a12[B - 1 + m] = make_float2(pr, pi);
+    if (m) a12[B - 1 - m] = make_float2(nr, ni);
   }
   __syncthreads();
-  // the cut-off at t < n0: convolution with the Dirichlet kernel, only for the bins the filter keeps
-  for (int idx = tid; idx < 3 * K; idx += kDirThreads) {
-    const int f = idx / K, k = idx - f * K - kc;
-    const float2 *dk = sdn + dm + k;                             // dk[-m] = Dn[k - m]
-    float sr = 0.0f, si = 0.0f;
-    if (f < 2) {
-      // real field: A[-m] = conj(A[m])
-      const float2 *a = f == 0 ? a1 : a2;
-      const float2 d0 = dk[0];
-      sr = a[0].x * d0.x;                                        // A[0] is real
-      si = a[0].x * d0.y;
-      for (int m = 1; m < B; ++m) {
-        const float2 am = a[m], dn_ = dk[-m], dp = dk[m];
-        // am * dn_ + conj(am) * dp
-        sr = fmaf(am.x, dn_.x + dp.x, fmaf(-am.y, dn_.y - dp.y, sr));
-        si = fmaf(am.x, dn_.y + dp.y, fmaf(am.y, dn_.x - dp.x, si));
-      }
-    } else {
-      for (int m = -(B - 1); m < B; ++m) {
-        const float2 am = a12[m + B - 1], d = dk[-m];
-        sr = fmaf(am.x, d.x, fmaf(-am.y, d.y, sr));
-        si = fmaf(am.x, d.y, fmaf(am.y, d.x, si));
-      }
+  // ---- step 3: the cut-off at t < n0 = convolution with the Dirichlet kernel, bins |k| <= kc only
+  const int KP = (kc + 2) / 2;                                 // k pairs (0,1), (2,3), ... covering 0 .. kc
+  const int M = 2 * B - 1;                                     // terms m = -(B-1) .. B-1
+  int G = kDirThreads / KP;
+  G = G < 1 ? 1 : (G > kDirG ? kDirG : G);
+  const int chunk = (M + G - 1) / G;
+  for (int item = tid; item < G * KP; item += kDirThreads) {
+    const int g = item / KP, kp = item - g * KP;
+    const int k0 = 2 * kp;
+    const int mi0 = g * chunk, mi1 = min(M, mi0 + chunk);      // m index range (m = mi - (B - 1))
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.0f;
+    // windows: dA0 = Dn[k0 - m], dA1 = Dn[k0 + 1 - m]; dB0 = Dn[-k0 - m], dB1 = Dn[-k0 - 1 - m]
+    const int m_first = mi0 - (B - 1);
+    const float2 *pa = sdn + dm + k0 - m_first;                // pa[-(mi - mi0)] = Dn[k0 - m]
+    const float2 *pb = sdn + dm - k0 - m_first;                // pb[-(mi - mi0)] = Dn[-k0 - m]
+    float2 dA1 = pa[1], dB0 = pb[0];
+    for (int mi = mi0; mi < mi1; ++mi) {
+      const int o = mi - mi0;
+      const float2 dA0 = pa[-o], dB1 = pb[-o - 1];
+      const float2 x1m = a1[mi], x2m = a2[mi], xc = a12[mi];   // broadcasts (a warp shares its chunk)
+      // P1 at k0, k0 + 1
+      acc[0] = fmaf(x1m.x, dA0.x, fmaf(-x1m.y, dA0.y, acc[0]));  acc[1] = fmaf(x1m.x, dA0.y, fmaf(x1m.y, dA0.x, acc[1]));
+      acc[2] = fmaf(x1m.x, dA1.x, fmaf(-x1m.y, dA1.y, acc[2]));  acc[3] = fmaf(x1m.x, dA1.y, fmaf(x1m.y, dA1.x, acc[3]));
+      // P2 at k0, k0 + 1
+      acc[4] = fmaf(x2m.x, dA0.x, fmaf(-x2m.y, dA0.y, acc[4]));  acc[5] = fmaf(x2m.x, dA0.y, fmaf(x2m.y, dA0.x, acc[5]));
+      acc[6] = fmaf(x2m.x, dA1.x, fmaf(-x2m.y, dA1.y, acc[6]));  acc[7] = fmaf(x2m.x, dA1.y, fmaf(x2m.y, dA1.x, acc[7]));
+      // C at k0, k0 + 1, -k0, -k0 - 1
+      acc[8] = fmaf(xc.x, dA0.x, fmaf(-xc.y, dA0.y, acc[8]));    acc[9] = fmaf(xc.x, dA0.y, fmaf(xc.y, dA0.x, acc[9]));
+      acc[10] = fmaf(xc.x, dA1.x, fmaf(-xc.y, dA1.y, acc[10]));  acc[11] = fmaf(xc.x, dA1.y, fmaf(xc.y, dA1.x, acc[11]));
+      acc[12] = fmaf(xc.x, dB0.x, fmaf(-xc.y, dB0.y, acc[12]));  acc[13] = fmaf(xc.x, dB0.y, fmaf(xc.y, dB0.x, acc[13]));
+      acc[14] = fmaf(xc.x, dB1.x, fmaf(-xc.y, dB1.y, acc[14]));  acc[15] = fmaf(xc.x, dB1.y, fmaf(xc.y, dB1.x, acc[15]));
+      dA1 = dA0;      // Dn[k0 + 1 - (m + 1)] = Dn[k0 - m]
+      dB0 = dB1;      // Dn[-k0 - (m + 1)]    = Dn[-k0 - 1 - m]
     }
-    out[f][k + kc] = make_float2(sr, si);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) part[g][q][kp] = make_float2(acc[2 * q], acc[2 * q + 1]);
   }
   __syncthreads();
   float4 *srow = spec + (pair * S + s) * (int64_t)kN;
-  for (int kk = tid; kk < K; kk += kDirThreads) {
-    const int k = kk - kc;
-    const float2 p1 = out[0][kk], p2 = out[1][kk], c = out[2][kk];
-    // P = |W1|^2 + i |W2|^2 travels as one complex field; 1/s and the 1/N of the inverse ride in g
+  // bins 0 .. kc and -1 .. -kc: P = |W1|^2 + i |W2|^2 travels as one complex field; 1/s and the 1/N of
+  // the inverse ride in g
+  for (int kk = tid; kk <= 2 * kc; kk += kDirThreads) {
+    const int k = kk <= kc ? kk : kc - kk;                     // 0 .. kc, then -1 .. -kc
+    const int ka = k < 0 ? -k : k, kp = ka >> 1, odd = ka & 1;
+    float2 p1 = make_float2(0.0f, 0.0f), p2 = p1, c = p1;
+    for (int g = 0; g < G; ++g) {                              // fixed order: reproducible sums
+      const float2 v1 = part[g][odd][kp], v2 = part[g][2 + odd][kp], vc = part[g][(k < 0 ? 6 : 4) + odd][kp];
+      p1.x += v1.x; p1.y += v1.y; p2.x += v2.x; p2.y += v2.y; c.x += vc.x; c.y += vc.y;
+    }
+    if (k < 0) { p1.y = -p1.y; p2.y = -p2.y; }                 // Hermitian: P1^[-k] = conj P1^[k]
     const float g = ex2(fmaf(rp.gcoef, (float)(k * k), -12.0f)) * rp.inv_s;
     srow[k >= 0 ? k : kN + k] = make_float4((p1.x - p2.y) * g, c.x * g, (p1.y + p2.x) * g, c.y * g);
   }
@@ -735,7 +775,7 @@ int wct_fast_try(const float2 *d_xhat, int64_t pairs, int n0, int N, double dt, 
   int s_split = S;
   std::vector<DRow> drows(S);
   if (smooth && !d_phase && !d_w12) {
-    int bmax = 72;      // measured break-even against the transform rows (WTB_MC_DIRECT_B overrides, 0 = off)
+    int bmax = 128;     // flat from 128 to 192 bins (measured); 128 keeps the kernel at 32 KB of shared memory (WTB_MC_DIRECT_B overrides, 0 = off)
     if (const char *e = std::getenv("WTB_MC_DIRECT_B")) bmax = std::min(std::atoi(e), kDirB);
     for (int q = S - 1; q >= 0; --q) {
       const double a = ax.scales[q] / dt * 2.0 * kPi / kN;

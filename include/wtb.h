@@ -40,6 +40,8 @@ extern "C" {
 #define WTB_NOISE_WHITE  (1 << 3)  /* Monte Carlo surrogates: white instead of AR(1) */
 #define WTB_GENERIC_ONLY (1 << 4)  /* force the generic (any pow2 N) kernels; testing */
 #define WTB_PLANE_COMPLEX (1 << 5) /* wtb_ratio_planes: the input plane is complex (|z|^2 is formed first) */
+#define WTB_FFT_NO_PAD   (1 << 6)  /* Monte Carlo: transform the surrogates at their own length (pycwt with
+                                      mkl_fft, the reference's conda install) instead of the next power of two */
 
 /* mother wavelets of wtb_cwt / wtb_cwt_axes_mother (pycwt.mothers) */
 #define WTB_MORLET 0   /* param = f0 */
@@ -87,8 +89,12 @@ uint64_t wtb_scratch_bytes(void);
 int wtb_cwt_axes(int n0, double dt, double dj, double s0, int J, double f0,
                  int *J_out, double *scales, double *freqs, double *coi);
 
-/* Batched Morlet CWT.  x: [batch, n0] real.  nfft: FFT length (power of two
- * >= n0; pycwt's scipy.fftpack path pads to 2^ceil(log2 n0)).  Outputs (either
+/* Batched Morlet CWT.  x: [batch, n0] real.  nfft: FFT length >= n0.  pycwt's scipy.fftpack
+ * path (the reference's pip / uv install) pads to 2^ceil(log2 n0); its mkl_fft path (the conda
+ * install, environment.yml:126) transforms at nfft = n0.  Powers of two run the FFT kernels
+ * (fused FP32 fast paths at 512 / 1024 / 2048 / 4096); any other length runs Bluestein's chirp-z
+ * transform over the next power of two >= 2 nfft - 1 in the generic kernels (nfft <= 2048 in
+ * FP64, <= 4096 in FP32).  Outputs (either
  * may be NULL): power_out [batch, S, n0] real = |W|^2; coef_out [batch, S, n0]
  * complex = W.  S = J+1 with scales s0*2^(j*dj).  No normalisation of x. */
 int wtb_cwt_morlet(const void *x, int64_t batch, int n0, int nfft,

@@ -6,6 +6,7 @@ for a clean error where there is none."""
 import numpy as np
 import pytest
 
+from conftest import normwise_close
 from oracle import modwt_oracle as mo
 from oracle import pycwt_oracle as po
 from oracle import pywt_oracle as pw
@@ -152,3 +153,63 @@ def test_shutdown_releases_and_next_call_rebuilds(shim):
 def _la8():
     from wavelet_transformer_b200 import pywt_compat as pywt
     return pywt.Wavelet("sym4")
+
+
+# ---- un-padded transforms: pycwt with mkl_fft (the reference's conda install, environment.yml:126)
+@pytest.fixture()
+def no_padding(shim):
+    shim.set_fft_padding("none")
+    yield shim
+    shim.set_fft_padding("pow2")
+
+
+@pytest.mark.parametrize("n0", [565, 1346, 97, 1000])
+def test_cwt_unpadded_lengths_fp64(no_padding, series, n0):
+    """nfft = n0 (any length): Bluestein's chirp-z transform in the generic kernels against the
+    oracle's pad_pow2=False path, FP64 at 1e-10 and FP32 at the 1e-4 gate."""
+    shim = no_padding
+    x = np.random.default_rng(n0).standard_normal(n0).cumsum()
+    x = (x - x.mean()) / x.std()
+    W_ref = po.cwt(x, DT, 1 / 12, 2 * DT, -1, pad_pow2=False)[0]
+    W_pad = po.cwt(x, DT, 1 / 12, 2 * DT, -1, pad_pow2=True)[0]
+    _, W = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=True, want_power=False, want_coef=True)
+    assert np.abs(W - W_ref).max() <= 1e-10 * np.abs(W_ref).max()
+    if n0 & (n0 - 1):
+        assert np.abs(W_pad - W_ref).max() > 1e-6 * np.abs(W_ref).max()       # the two conventions do differ
+    p32, _ = shim.cwt_morlet(np.stack([x, x[::-1]]), DT, 1 / 12, 2 * DT, -1, f64=False)
+    ok, worst = normwise_close(p32[0], np.abs(W_ref) ** 2, 1e-4)
+    assert ok, worst
+    # explicit nfft overrides the global rule
+    _, W2 = shim.cwt_morlet(x, DT, 1 / 12, 2 * DT, -1, f64=True, want_power=False, want_coef=True,
+                            nfft=shim.next_pow2(n0))
+    assert np.abs(W2 - W_pad).max() <= 1e-10 * np.abs(W_pad).max()
+
+
+def test_wct_xwt_and_significance_unpadded(no_padding, series):
+    shim = no_padding
+    from wavelet_transformer_b200 import pycwt_compat as wavelet
+    y1 = 100 * np.diff(np.log(series["cpi_value"]))[-565:]
+    y2 = series["pair_expectation"]
+    WCT, aWCT, coi, freq, _ = po.wct(y1, y2, DT, dj=1 / 8, s0=2 * DT, J=-1, sig=False, pad_pow2=False)
+    got, phase, c2, f2, _ = wavelet.wct(y1, y2, DT, dj=1 / 8, s0=2 * DT, J=-1, sig=False)
+    assert np.abs(got - WCT).max() <= 1e-10
+    assert np.abs(np.angle(np.exp(1j * (phase - aWCT)))).max() <= 1e-8
+    W12, *_ = po.xwt(y1, y2, DT, dj=1 / 8, s0=2 * DT, J=-1, pad_pow2=False)
+    X12, *_ = wavelet.xwt(y1, y2, DT, dj=1 / 8, s0=2 * DT, J=-1)
+    assert np.abs(X12 - W12).max() <= 1e-10 * np.abs(W12).max()
+    # Monte Carlo with injected surrogates at their own length (N = 601, not a power of two)
+    dj, s0, J = 1 / 4, 2 * DT, 22
+    N, maxscale = shim.wct_mc_geometry(DT, dj, s0, J)
+    assert N & (N - 1)
+    rng = np.random.default_rng(4)
+    sur = np.stack([np.stack([po.rednoise(N, 0.8, 1, rng), po.rednoise(N, 0.6, 1, rng)]) for _ in range(4)])
+    sig_ref, hist_ref = po.wct_significance(0.8, 0.6, DT, dj, s0, J, mc_count=4, surrogates=sur, return_hist=True,
+                                            pad_pow2=False)
+    hist = shim.wct_mc_hist(0.8, 0.6, DT, dj, s0, J, mc_count=4, surrogates=sur, f64=True)
+    assert hist.sum() == hist_ref.sum() and np.abs(hist.astype(np.int64) - hist_ref).sum() <= 4
+    h32 = shim.wct_mc_hist(0.8, 0.6, DT, dj, s0, J, mc_count=4, surrogates=sur, f64=False)
+    cdf = lambda h: h.cumsum(axis=1) / np.maximum(h.sum(axis=1, keepdims=True), 1)
+    assert h32.sum() == hist_ref.sum() and np.abs(cdf(h32) - cdf(hist_ref)).max() <= 2e-3
+    shim.set_fft_padding("pow2")
+    padded = shim.wct_mc_hist(0.8, 0.6, DT, dj, s0, J, mc_count=4, surrogates=sur, f64=True)
+    assert not np.array_equal(padded, hist)

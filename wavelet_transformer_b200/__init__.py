@@ -16,7 +16,7 @@ Layout
     engine.py         batched / multi-GPU entry points (series and Monte Carlo shards)
 """
 
-from ._shim import (WaveletEngineError, device_count, get_precision, init, lib_path,  # noqa: F401
-                    set_precision, shutdown)
+from ._shim import (WaveletEngineError, device_count, get_fft_padding, get_precision, gpu_count, init,  # noqa: F401
+                    init_multi, lib_path, set_fft_padding, set_precision, shutdown)
 
 __version__ = "0.1.0"

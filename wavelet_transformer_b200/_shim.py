@@ -21,6 +21,7 @@ COI_MASK = 1 << 2
 NOISE_WHITE = 1 << 3
 GENERIC_ONLY = 1 << 4
 PLANE_COMPLEX = 1 << 5
+FFT_NO_PAD = 1 << 6
 NBINS = 1000
 
 _lock = threading.Lock()
@@ -42,6 +43,28 @@ def set_precision(name: str) -> None:
 
 def get_precision() -> str:
     return _precision
+
+
+_fft_pad = os.environ.get("WTB_FFT_PAD", "pow2").lower()
+
+
+def set_fft_padding(mode: str) -> None:
+    """'pow2' (default): every transform is zero-padded to the next power of two, as pycwt does
+    on top of scipy.fftpack -- the reference's pip / uv install.  'none': transforms run at the
+    series' own length, as pycwt does when mkl_fft is importable -- the reference's conda
+    install (environment.yml:126).  The two give different numbers near the edges."""
+    global _fft_pad
+    if mode not in ("pow2", "none"):
+        raise ValueError("fft padding must be 'pow2' or 'none'")
+    _fft_pad = mode
+
+
+def get_fft_padding() -> str:
+    return _fft_pad
+
+
+def default_nfft(n0: int) -> int:
+    return next_pow2(n0) if _fft_pad == "pow2" else max(int(n0), 2)
 
 
 def _dtype(f64):
@@ -219,7 +242,7 @@ def cwt(x, dt, dj, s0, J, mother=MORLET, param=6.0, *, nfft=None, f64=None, want
     batch, n0 = x2.shape
     Jr, _, _, _ = cwt_axes_mother(n0, dt, dj, s0, J, mother, param)
     S = Jr + 1
-    nfft = int(nfft) if nfft else next_pow2(n0)
+    nfft = int(nfft) if nfft else default_nfft(n0)
     flags = (F64 if f64 else 0) | (COI_MASK if coi_mask else 0) | (GENERIC_ONLY if generic_only else 0)
     power = np.empty((batch, S, n0), dtype=rt) if want_power else None
     coef = np.empty((batch, S, n0), dtype=np.complex128 if f64 else np.complex64) if want_coef else None
@@ -257,7 +280,7 @@ def cwt_morlet(x, dt, dj, s0, J, f0=6.0, *, nfft=None, f64=None, want_power=True
     batch, n0 = x2.shape
     Jr, _, _, _ = cwt_axes(n0, dt, dj, s0, J, f0)
     S = Jr + 1
-    nfft = int(nfft) if nfft else next_pow2(n0)
+    nfft = int(nfft) if nfft else default_nfft(n0)
     flags = (F64 if f64 else 0) | (COI_MASK if coi_mask else 0) | (GENERIC_ONLY if generic_only else 0)
     power = np.empty((batch, S, n0), dtype=rt) if want_power else None
     coef = np.empty((batch, S, n0), dtype=np.complex128 if f64 else np.complex64) if want_coef else None
@@ -272,7 +295,7 @@ def cwt_morlet(x, dt, dj, s0, J, f0=6.0, *, nfft=None, f64=None, want_power=True
 def cwt_power_device(x_ptr, batch, n0, dt, dj, s0, J, f0, power_ptr, *, nfft=None, f64=False,
                      stream=0, generic_only=False):
     """Device-resident variant: raw device addresses, asynchronous on `stream`."""
-    nfft = int(nfft) if nfft else next_pow2(n0)
+    nfft = int(nfft) if nfft else default_nfft(n0)
     flags = DEVICE_PTRS | (F64 if f64 else 0) | (GENERIC_ONLY if generic_only else 0)
     _check(lib().wtb_cwt_morlet(_ptr(int(x_ptr)), batch, n0, nfft, dt, dj, s0, int(J), f0, flags,
                                 _ptr(int(power_ptr)), None, C.c_void_p(int(stream))), "wtb_cwt_morlet")
@@ -384,7 +407,7 @@ def xwt_wct(y1, y2, dt, dj, s0, J, f0=6.0, *, nfft=None, f64=None, want_wct=True
     batch, n0 = a.shape
     Jr, _, _, _ = cwt_axes(n0, dt, dj, s0, J, f0)
     S = Jr + 1
-    nfft = int(nfft) if nfft else next_pow2(n0)
+    nfft = int(nfft) if nfft else default_nfft(n0)
     wct = np.empty((batch, S, n0), dtype=rt) if want_wct else None
     phase = np.empty((batch, S, n0), dtype=rt) if want_phase else None
     w12 = np.empty((batch, S, n0), dtype=np.complex128 if f64 else np.complex64) if want_w12 else None
@@ -418,7 +441,8 @@ def wct_mc_hist(a1, a2, dt, dj, s0, J, f0=6.0, *, mc_first=0, mc_count=300, seed
         sur = np.ascontiguousarray(surrogates, dtype=_dtype(f64))
         if sur.shape != (mc_count, 2, nsurr):
             raise ValueError(f"surrogates must have shape ({mc_count}, 2, {nsurr}), got {sur.shape}")
-    flags = (F64 if f64 else 0) | (NOISE_WHITE if white else 0) | (GENERIC_ONLY if generic_only else 0)
+    flags = ((F64 if f64 else 0) | (NOISE_WHITE if white else 0) | (GENERIC_ONLY if generic_only else 0)
+             | (FFT_NO_PAD if _fft_pad == "none" else 0))
     _check(lib().wtb_wct_mc_hist(a1, a2, dt, dj, s0, int(J), f0, int(mc_first), int(mc_count),
                                  C.c_uint64(int(seed)), _ptr(sur), flags, _ptr(hist), None), "wtb_wct_mc_hist")
     return hist
@@ -463,7 +487,8 @@ def wct_significance(a1, a2, dt, dj, s0, J, f0=6.0, *, level=0.95, mc_count=300,
         sur = np.ascontiguousarray(surrogates, dtype=_dtype(f64))
         if sur.shape != (mc_count, 2, nsurr):
             raise ValueError(f"surrogates must have shape ({mc_count}, 2, {nsurr}), got {sur.shape}")
-    flags = (F64 if f64 else 0) | (NOISE_WHITE if white else 0) | (GENERIC_ONLY if generic_only else 0)
+    flags = ((F64 if f64 else 0) | (NOISE_WHITE if white else 0) | (GENERIC_ONLY if generic_only else 0)
+             | (FFT_NO_PAD if _fft_pad == "none" else 0))
     sig = np.empty(S)
     hist = np.zeros((S, NBINS), dtype=np.uint64) if return_hist else None
     _check(lib().wtb_wct_significance(a1, a2, dt, dj, s0, int(J), f0, float(level), int(mc_count),

@@ -143,6 +143,10 @@ size_t scratch_bytes_held();
 // Twiddle table exp(-2*pi*i*k/N), k in [0,N), in precision T; cached per (device,N).
 template <typename T> int twiddles(int N, const cplx<T> **out);
 
+// Chirp tables of Bluestein's algorithm for length n over work length M (fft_block.cuh), cached
+// per (device, n, M) like the twiddles.
+template <typename T> int bluestein_tables(int n, int M, const cplx<T> **chirp, const cplx<T> **chat);
+
 int sm_count();               // SMs of current_device()
 
 // ---- multi-GPU pool (multi.cu): one worker thread + stream per device -------------------

@@ -24,14 +24,15 @@ int fwd_fft_4096_try(const float *d_y, int64_t nseries, int n0, int N, float2 *d
 
 // One CTA = one (series, chunk of scales).  smem: 2 * N complex.
 template <typename T>
-__global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
+__global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, FftPlan<T> plan, int S,
                            int chunk, const double *__restrict__ scales, double dt, double f0,
-                           const cplx<T> *__restrict__ tw, T *__restrict__ power,
+                           T *__restrict__ power,
                            cplx<T> *__restrict__ coef, int coi_mask, double coi_c, double flambda,
                            int mother, int order, T pre_re, T pre_im) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T> *a = reinterpret_cast<cplx<T> *>(smem_raw);
-  cplx<T> *b = a + N;
+  cplx<T> *b = a + plan.M;
+  const int N = plan.n;
   const int nchunks = (S + chunk - 1) / chunk;
   const int64_t row = blockIdx.x / nchunks;
   const int c = blockIdx.x % nchunks;
@@ -67,7 +68,7 @@ __global__ void k_cwt_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
       }
     }
     __syncthreads();
-    cplx<T> *r = block_fft<T, +1>(a, b, N, log2N, tw);
+    cplx<T> *r = plan_fft<T, +1>(a, b, plan);
     const int64_t obase = (row * S + s) * (int64_t)n0;
     const double period = 1.0 / (1.0 / (flambda * sc));
     for (int t = threadIdx.x; t < n0; t += blockDim.x) {
@@ -96,20 +97,20 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
     int rc = cwt_fast_try((const float *)d_x, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
     if (rc != 1) return rc;
   }
-  const size_t smem = 2 * sizeof(cplx<T>) * (size_t)N;
+  FftPlan<T> plan;
+  WTB_TRY(make_plan<T>(N, &plan));
+  const size_t smem = 2 * sizeof(cplx<T>) * (size_t)plan.M;
   WTB_REQUIRE(smem <= 227 * 1024, WTB_EUNSUPPORTED,
-              "nfft=%d needs %zu B of shared memory per CTA (limit 227 KB): max nfft is %d for %s",
-              N, smem, sizeof(T) == 4 ? 8192 : 4096, sizeof(T) == 4 ? "float" : "double");
-  const cplx<T> *tw = nullptr;
-  WTB_TRY(twiddles<T>(N, &tw));
+              "nfft=%d needs %zu B of shared memory per CTA (limit 227 KB): a power of two up to %d, any other "
+              "length up to %d for %s", N, smem, sizeof(T) == 4 ? 8192 : 4096, sizeof(T) == 4 ? 4096 : 2048,
+              sizeof(T) == 4 ? "float" : "double");
   void *scratch = nullptr;
   const size_t sc_bytes = ((sizeof(double) * S + 255) / 256) * 256;
   WTB_TRY(arena_reserve(sc_bytes + sizeof(cplx<T>) * (size_t)batch * N, &scratch));
   double *d_scales = (double *)scratch;
   cplx<T> *d_xhat = (cplx<T> *)((char *)scratch + sc_bytes);
   WTB_CUDA(cudaMemcpyAsync(d_scales, ax.scales.data(), sizeof(double) * S, cudaMemcpyHostToDevice, st));
-  const int log2N = ilog2(N);
-  const int threads = N >= 1024 ? 256 : (N >= 256 ? 128 : 64);
+  const int threads = plan.M >= 1024 ? 256 : (plan.M >= 256 ? 128 : 64);
   WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   WTB_CUDA(cudaFuncSetAttribute(k_cwt_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int fwd_rc = 1;
@@ -119,7 +120,7 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
     if (fwd_rc < 0) return fwd_rc;
   }
   if (fwd_rc == 1) {
-    k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, N, log2N, tw, d_xhat);
+    k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, plan, d_xhat);
     WTB_LAUNCH_CHECK();
   }
   if constexpr (sizeof(T) == 4) {
@@ -143,7 +144,7 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
   double pre_re, pre_im;
   mother_prefactor(mo, &pre_re, &pre_im);
   k_cwt_rows<T><<<(unsigned)(batch * nchunks), threads, smem, st>>>(
-      d_xhat, n0, N, log2N, S, chunk, d_scales, dt, f0, tw, d_power, d_coef,
+      d_xhat, n0, plan, S, chunk, d_scales, dt, f0, d_power, d_coef,
       (flags & WTB_COI_MASK) ? 1 : 0, mother_flambda(mo) * mother_coi(mo) * dt, mother_flambda(mo), mo.kind,
       (int)mo.param, T(pre_re), T(pre_im));
   WTB_LAUNCH_CHECK();
@@ -204,9 +205,9 @@ extern "C" int wtb_cwt(const void *x, int64_t batch, int n0, int nfft, double dt
                        int mother, double param, int flags, void *power_out, void *coef_out, void *stream) {
   WTB_REQUIRE(x && batch >= 0 && n0 > 0, WTB_EINVAL, "wtb_cwt: bad x/batch/n0");
   WTB_REQUIRE(power_out || coef_out, WTB_EINVAL, "wtb_cwt: no output requested");
-  WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
-              "nfft=%d must be a power of two >= n0=%d (pycwt's scipy.fftpack padding rule); "
-              "the un-padded mkl_fft variant is not supported", nfft, n0);
+  WTB_REQUIRE(nfft >= n0 && nfft >= 2, WTB_EINVAL,
+              "nfft=%d must be >= n0=%d (a power of two: pycwt's scipy.fftpack padding rule; n0 itself: "
+              "the un-padded mkl_fft rule)", nfft, n0);
   WTB_ENTER(flags, x, stream);
   Mother mo;
   mo.kind = mother;

@@ -76,4 +76,55 @@ __device__ cplx<T> *block_fft(cplx<T> *a, cplx<T> *b, int N, int log2N,
   return in;
 }
 
+// ---- transforms of any length ------------------------------------------------------------
+// pycwt pads every transform to a power of two only when mkl_fft is absent (the reference's pip /
+// uv install); its conda environment (environment.yml:126, mkl_fft) transforms the series at its
+// own length.  A plan covers both: a power-of-two length n is one Stockham FFT; any other n is
+// Bluestein's chirp-z identity  t k = (t^2 + k^2 - (k - t)^2) / 2,
+//   X[k] = c[k] * sum_t (x[t] c[t]) conj(c)[k - t],   c[t] = exp(-i pi t^2 / n),
+// i.e. one circular convolution of length M = 2^m >= 2 n - 1 with a fixed kernel whose transform
+// is tabulated (chat, 1/M folded in): two length-M FFTs and three pointwise passes.
+template <typename T> struct FftPlan {
+  int n = 0;                          // transform length
+  int M = 0;                          // work length: n itself when it is a power of two
+  int log2M = 0;
+  const cplx<T> *tw = nullptr;        // exp(-2 pi i k / M)
+  const cplx<T> *chirp = nullptr;     // [n]  exp(-i pi t^2 / n); null for a power of two
+  const cplx<T> *chat = nullptr;      // [M]  FFT_M of the wrapped conj chirp, divided by M
+};
+
+// `a` holds the n inputs (capacity M, like `b`); all threads call; the result pointer (n valid
+// values) is returned after a barrier.  SIGN = -1 forward, +1 inverse (unnormalised).
+template <typename T, int SIGN>
+__device__ cplx<T> *plan_fft(cplx<T> *a, cplx<T> *b, const FftPlan<T> &p) {
+  using C = cplx<T>;
+  if (!p.chirp) return block_fft<T, SIGN>(a, b, p.M, p.log2M, p.tw);
+  for (int t = threadIdx.x; t < p.M; t += blockDim.x) {
+    C v = mk<T>(T(0), T(0));
+    if (t < p.n) {
+      C c = p.chirp[t];
+      if (SIGN > 0) c.y = -c.y;
+      v = cmul(a[t], c);
+    }
+    a[t] = v;
+  }
+  __syncthreads();
+  C *r = block_fft<T, -1>(a, b, p.M, p.log2M, p.tw);
+  C *other = (r == a) ? b : a;
+  for (int k = threadIdx.x; k < p.M; k += blockDim.x) {
+    C h = p.chat[k];
+    if (SIGN > 0) h.y = -h.y;           // the kernel is even, so conj(chat) is the conjugate chirp's transform
+    r[k] = cmul(r[k], h);
+  }
+  __syncthreads();
+  C *z = block_fft<T, +1>(r, other, p.M, p.log2M, p.tw);
+  for (int t = threadIdx.x; t < p.n; t += blockDim.x) {
+    C c = p.chirp[t];
+    if (SIGN > 0) c.y = -c.y;
+    z[t] = cmul(z[t], c);
+  }
+  __syncthreads();
+  return z;
+}
+
 }  // namespace wtb

@@ -1,6 +1,7 @@
 // Runtime plumbing of libwavelet_sm100a.so: errors, device binding, scratch
 // arenas, twiddle tables, and the small host-side pieces of the C ABI.
 #include <atomic>
+#include <tuple>
 #include <chrono>
 #include <cstdarg>
 
@@ -332,10 +333,89 @@ template <typename T> int twiddles(int N, const cplx<T> **out) {
 template int twiddles<float>(int, const cplx<float> **);
 template int twiddles<double>(int, const cplx<double> **);
 
+// ---- Bluestein tables ----------------------------------------------------------------
+namespace {
+void host_fft(std::vector<long double> &re, std::vector<long double> &im) {   // in place, radix 2, forward
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  const long double pi = 3.141592653589793238462643383279502884L;
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const long double ang = -2.0L * pi / (long double)len;
+    for (size_t i = 0; i < n; i += len) {
+      for (size_t k = 0; k < len / 2; ++k) {
+        const long double wr = cosl(ang * k), wi = sinl(ang * k);
+        const size_t a = i + k, b = i + k + len / 2;
+        const long double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+        re[b] = re[a] - xr; im[b] = im[a] - xi;
+        re[a] += xr; im[a] += xi;
+      }
+    }
+  }
+}
+template <typename T> struct BsCache {
+  std::mutex mu;
+  std::map<std::tuple<int, int, int>, std::pair<void *, void *>> tab;
+};
+template <typename T> BsCache<T> &bs_cache() {
+  static BsCache<T> c;
+  return c;
+}
+}  // namespace
+
+template <typename T> int bluestein_tables(int n, int M, const cplx<T> **chirp, const cplx<T> **chat) {
+  BsCache<T> &c = bs_cache<T>();
+  std::lock_guard<std::mutex> lk(c.mu);
+  const auto key = std::make_tuple(tl_device, n, M);
+  auto it = c.tab.find(key);
+  if (it == c.tab.end()) {
+    const long double pi = 3.141592653589793238462643383279502884L;
+    std::vector<cplx<T>> hc(n), hh(M);
+    std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+    for (int t = 0; t < n; ++t) {
+      // pi t^2 / n with t^2 reduced modulo 2n in integers: the phase stays exact for any t
+      const long long q = ((long long)t * t) % (2LL * n);
+      const long double ang = pi * (long double)q / (long double)n;
+      hc[t] = mk<T>((T)cosl(ang), (T)-sinl(ang));          // exp(-i pi t^2 / n)
+      br[t] = cosl(ang); bi[t] = sinl(ang);                // conj chirp, wrapped: b[M - t] = b[t]
+      if (t) { br[M - t] = br[t]; bi[M - t] = bi[t]; }
+    }
+    host_fft(br, bi);
+    for (int k = 0; k < M; ++k) hh[k] = mk<T>((T)(br[k] / M), (T)(bi[k] / M));
+    void *d1 = nullptr, *d2 = nullptr;
+    WTB_CUDA(cudaMalloc(&d1, sizeof(cplx<T>) * n));
+    WTB_CUDA(cudaMalloc(&d2, sizeof(cplx<T>) * M));
+    WTB_CUDA(cudaMemcpy(d1, hc.data(), sizeof(cplx<T>) * n, cudaMemcpyHostToDevice));
+    WTB_CUDA(cudaMemcpy(d2, hh.data(), sizeof(cplx<T>) * M, cudaMemcpyHostToDevice));
+    it = c.tab.emplace(key, std::make_pair(d1, d2)).first;
+  }
+  *chirp = (const cplx<T> *)it->second.first;
+  *chat = (const cplx<T> *)it->second.second;
+  return WTB_OK;
+}
+template int bluestein_tables<float>(int, int, const cplx<float> **, const cplx<float> **);
+template int bluestein_tables<double>(int, int, const cplx<double> **, const cplx<double> **);
+
 void wct_fast_release();  // wct_fast.cu: the radix-16 twiddle tables
 void pool_shutdown();      // multi.cu
 
 static void free_tables() {
+  {
+    BsCache<float> &c = bs_cache<float>();
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto &kv : c.tab) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    c.tab.clear();
+  }
+  {
+    BsCache<double> &c = bs_cache<double>();
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto &kv : c.tab) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    c.tab.clear();
+  }
   {
     TwCache<float> &c = tw_cache<float>();
     std::lock_guard<std::mutex> lk(c.mu);

@@ -37,14 +37,15 @@ template <typename T> using vec4 = typename vec4_of<T>::type;
 // One CTA = one (pair, scale).  smem: 3 * N complex (U, V, tmp).
 // xhat: [pairs, 2, N].  tsm: [pairs, S, n0] vec4.  phase/w12 optional [pairs,S,n0].
 template <typename T>
-__global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int log2N, int S,
+__global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, FftPlan<T> plan, int S,
                            const double *__restrict__ scales, double dt, double f0,
-                           const cplx<T> *__restrict__ tw, vec4<T> *__restrict__ tsm,
+                           vec4<T> *__restrict__ tsm,
                            T *__restrict__ phase, cplx<T> *__restrict__ w12, int smooth) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx<T> *U = reinterpret_cast<cplx<T> *>(smem_raw);
-  cplx<T> *V = U + N;
-  cplx<T> *Tm = V + N;
+  cplx<T> *V = U + plan.M;
+  cplx<T> *Tm = V + plan.M;
+  const int N = plan.n;
   const int64_t pair = blockIdx.x / S;
   const int s = blockIdx.x % S;
   const cplx<T> *x1 = xhat + (pair * 2) * (int64_t)N;
@@ -60,9 +61,9 @@ __global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
   }
   __syncthreads();
   cplx<T> *r;
-  r = block_fft<T, +1>(U, Tm, N, log2N, tw);
+  r = plan_fft<T, +1>(U, Tm, plan);
   if (r != U) { Tm = U; U = r; }
-  r = block_fft<T, +1>(V, Tm, N, log2N, tw);
+  r = plan_fft<T, +1>(V, Tm, plan);
   if (r != V) { Tm = V; V = r; }
   // U = W1 row, V = W2 row (valid for t < n0; pycwt truncates before smoothing)
   const int64_t obase = (pair * S + s) * (int64_t)n0;
@@ -82,9 +83,9 @@ __global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
   }
   if (!smooth) return;
   __syncthreads();
-  r = block_fft<T, -1>(U, Tm, N, log2N, tw);
+  r = plan_fft<T, -1>(U, Tm, plan);
   if (r != U) { Tm = U; U = r; }
-  r = block_fft<T, -1>(V, Tm, N, log2N, tw);
+  r = plan_fft<T, -1>(V, Tm, plan);
   if (r != V) { Tm = V; V = r; }
   // Gaussian in the Fourier domain: exp(-0.5 (s/dt)^2 k^2), k = 2*pi*fftfreq(N)
   const T invN = T(1.0 / N);
@@ -97,9 +98,9 @@ __global__ void k_wct_rows(const cplx<T> *__restrict__ xhat, int n0, int N, int 
     V[k] = mk<T>(c.x * g, c.y * g);
   }
   __syncthreads();
-  r = block_fft<T, +1>(U, Tm, N, log2N, tw);
+  r = plan_fft<T, +1>(U, Tm, plan);
   if (r != U) { Tm = U; U = r; }
-  r = block_fft<T, +1>(V, Tm, N, log2N, tw);
+  r = plan_fft<T, +1>(V, Tm, plan);
   if (r != V) { Tm = V; V = r; }
   for (int t = threadIdx.x; t < n0; t += blockDim.x) {
     const cplx<T> p = U[t], c = V[t];
@@ -171,15 +172,16 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
                       cudaStream_t st) {
   const int S = ax.J + 1;
   const bool smooth = d_wct || d_hist;
-  const size_t smem_fwd = 2 * sizeof(cplx<T>) * (size_t)N;
-  const size_t smem_rows = 3 * sizeof(cplx<T>) * (size_t)N;
+  FftPlan<T> plan;
+  WTB_TRY(make_plan<T>(N, &plan));
+  const size_t smem_fwd = 2 * sizeof(cplx<T>) * (size_t)plan.M;
+  const size_t smem_rows = 3 * sizeof(cplx<T>) * (size_t)plan.M;
   WTB_REQUIRE(smem_rows <= 227 * 1024, WTB_EUNSUPPORTED,
-              "nfft=%d needs %zu B of shared memory per CTA (limit 227 KB): max nfft is %d for %s",
-              N, smem_rows, sizeof(T) == 4 ? 8192 : 4096, sizeof(T) == 4 ? "float" : "double");
+              "nfft=%d needs %zu B of shared memory per CTA (limit 227 KB): a power of two up to %d, any other "
+              "length up to %d for %s", N, smem_rows, sizeof(T) == 4 ? 8192 : 4096, sizeof(T) == 4 ? 4096 : 2048,
+              sizeof(T) == 4 ? "float" : "double");
   ScaleWin win;
   WTB_TRY(make_win(dj, &win));
-  const cplx<T> *tw = nullptr;
-  WTB_TRY(twiddles<T>(N, &tw));
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t b_sc = al(sizeof(double) * S);
   const size_t b_rng = al(sizeof(int) * S);
@@ -200,8 +202,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
     WTB_CUDA(cudaMemcpyAsync(d_tlo, h_tlo, sizeof(int) * S, cudaMemcpyHostToDevice, st));
     WTB_CUDA(cudaMemcpyAsync(d_thi, h_thi, sizeof(int) * S, cudaMemcpyHostToDevice, st));
   }
-  const int log2N = ilog2(N);
-  const int threads = N >= 1024 ? 256 : (N >= 256 ? 128 : 64);
+  const int threads = plan.M >= 1024 ? 256 : (plan.M >= 256 ? 128 : 64);
   WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
   WTB_CUDA(cudaFuncSetAttribute(k_wct_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
   WTB_REQUIRE(pairs * S < (1LL << 31) && pairs * 2 < (1LL << 31), WTB_EUNSUPPORTED, "batch too large");
@@ -212,7 +213,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
     if (fwd_rc < 0) return fwd_rc;
   }
   if (fwd_rc == 1) {
-    k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, N, log2N, tw, d_xhat);
+    k_fwd_fft<T><<<(unsigned)(pairs * 2), threads, smem_fwd, st>>>(d_y, n0, plan, d_xhat);
     WTB_LAUNCH_CHECK();
   }
   WTB_TRACE_POINT(st, "wct: forward transforms");
@@ -226,7 +227,7 @@ static int wct_device(const T *d_y, int64_t pairs, int n0, int N, double dt, dou
   }
   if (fast_rc == 1) {
     k_wct_rows<T><<<(unsigned)(pairs * S), threads, smem_rows, st>>>(
-        d_xhat, n0, N, log2N, S, d_scales, dt, f0, tw, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
+        d_xhat, n0, plan, S, d_scales, dt, f0, d_tsm, d_phase, d_w12, smooth ? 1 : 0);
     WTB_LAUNCH_CHECK();
     if (smooth) {
       const int64_t cols = pairs * n0;
@@ -403,7 +404,7 @@ static int mc_hist_entry(double a1, double a2, double dt, double dj, const Axes 
                          int nsurr, int maxscale, int64_t mc_first, int64_t mc_count, uint64_t seed,
                          const void *surrogates, int flags, uint64_t *hist, cudaStream_t st) {
   const int S = ax.J + 1;
-  const int N = 1 << ilog2(nsurr);
+  const int N = (flags & WTB_FFT_NO_PAD) ? nsurr : (1 << ilog2(nsurr));   // pycwt with / without mkl_fft
   std::vector<int> tlo, thi;
   std::vector<uint8_t> any;
   WTB_TRACE_POINT(st, "mc: entry");
@@ -476,8 +477,7 @@ extern "C" int wtb_xwt_wct(const void *y1, const void *y2, int64_t batch, int n0
                            void *phase_out, void *w12_out, void *stream) {
   WTB_REQUIRE(y1 && y2 && batch >= 0 && n0 > 0, WTB_EINVAL, "wtb_xwt_wct: bad inputs");
   WTB_REQUIRE(wct_out || phase_out || w12_out, WTB_EINVAL, "wtb_xwt_wct: no output requested");
-  WTB_REQUIRE(is_pow2(nfft) && nfft >= n0 && nfft >= 2, WTB_EUNSUPPORTED,
-              "nfft=%d must be a power of two >= n0=%d", nfft, n0);
+  WTB_REQUIRE(nfft >= n0 && nfft >= 2, WTB_EINVAL, "nfft=%d must be >= n0=%d", nfft, n0);
   WTB_ENTER(flags, y1, stream);
   Axes ax;
   WTB_TRY(resolve_axes(n0, dt, dj, s0, J, f0, &ax));

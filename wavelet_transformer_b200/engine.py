@@ -145,7 +145,7 @@ def wct_batch_resident(y1, y2, dt, dj, s0, J, f0=6.0, signif=None):
     stream = torch.cuda.current_stream(y1.device).cuda_stream
     import ctypes as C
     _shim._check(_shim.lib().wtb_xwt_wct(C.c_void_p(y1.data_ptr()), C.c_void_p(y2.data_ptr()), batch, n0,
-                                         _shim.next_pow2(n0), dt, dj, s0, Jr, f0, flags, C.c_void_p(wct.data_ptr()),
+                                         _shim.default_nfft(n0), dt, dj, s0, Jr, f0, flags, C.c_void_p(wct.data_ptr()),
                                          C.c_void_p(phase.data_ptr()), None, C.c_void_p(stream)), "wtb_xwt_wct")
     u, v = phase_arrows_resident(phase)
     out = {"coherence": wct, "phase": phase, "phase_diff_u": u, "phase_diff_v": v, "period": 1.0 / freqs, "coi": coi,

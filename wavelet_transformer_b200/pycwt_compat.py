@@ -260,7 +260,7 @@ def cwt(signal, dt, dj=1 / 12, s0=-1, J=-1, wavelet="morlet", freqs=None):
     W = np.asarray(W, dtype=np.complex128)
     # Side outputs pycwt also returns and the reference discards (src/cwt.py:109):
     # one O(N log N) host FFT, outside the hot path.
-    N = _shim.next_pow2(n0)
+    N = _shim.default_nfft(n0)
     sft = np.fft.fft(x, N)
     ftfreqs = 2 * np.pi * np.fft.fftfreq(N, dt)
     return W, sj, fr, coi, sft[1:N // 2] / N ** 0.5, ftfreqs[1:N // 2] / (2 * np.pi)

@@ -551,22 +551,30 @@ def bench_filterbank(c):
 def run_gpu(args):
     c = setup_gpu(args)
     sampler = ClockSampler(c.local) if c.rank == 0 else None
+    def guarded(name, fn):
+        """Secondary measurements must never cost the primary line: a failure is recorded, not raised
+        (every rank takes the same path -- the secondaries contain collectives only through barriers)."""
+        try:
+            return fn()
+        except Exception as exc:  # noqa: BLE001
+            return {"error": f"{name}: {type(exc).__name__}: {exc}"}
+
     if args.workload == "wct_mc":
         line = bench_mc(c, args, sampler)
         if not args.no_secondary:
             sampler2 = ClockSampler(c.local) if c.rank == 0 else None
-            sec = bench_cwt(c, args, sampler2, steps=args.secondary_steps, warmup=3)
-            line["secondary"] = sec
-            line["secondary_filterbank"] = bench_filterbank(c)
+            line["secondary"] = guarded("cfg4 secondary", lambda: bench_cwt(c, args, sampler2, steps=args.secondary_steps,
+                                                                           warmup=3))
+            line["secondary_filterbank"] = guarded("filterbank secondary", lambda: bench_filterbank(c))
     else:
         line = bench_cwt(c, args, sampler)
         if not args.no_secondary:
-            line["secondary_filterbank"] = bench_filterbank(c)
+            line["secondary_filterbank"] = guarded("filterbank secondary", lambda: bench_filterbank(c))
     if c.rank == 0:
         if c.world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_budget)
-            if "secondary" in line:
-                line["secondary"]["cpu_baseline"] = cpu_baseline("cwt", args.cpu_budget)
+            line["cpu_baseline"] = guarded("cpu baseline", lambda: cpu_baseline(args.workload, args.cpu_budget))
+            if "secondary" in line and "error" not in line["secondary"]:
+                line["secondary"]["cpu_baseline"] = guarded("cpu baseline (cwt)", lambda: cpu_baseline("cwt", args.cpu_budget))
         c.real_stdout.write(json.dumps(line) + "\n")
         c.real_stdout.flush()
     if c.world > 1:

@@ -150,3 +150,48 @@ def test_published_chi_square_and_red_noise_values():
     assert np.allclose(theor, want, rtol=1e-14) and np.allclose(signif, want * 5.991464547107979 / 2, rtol=1e-12)
     # zero lag-1 autocorrelation: white noise, flat spectrum of the signal's variance
     assert np.allclose(po.significance(2.0, 0.25, np.array([1.0, 4.0]), 0, 0.0)[1], 2.0)
+
+
+def test_cwt_matches_the_time_domain_definition():
+    """Torrence & Compo (1998) eq. 2, evaluated directly: W_n(s) = sum_n' x_n' conj(psi((n' - n) dt / s))
+    with psi(eta) = sqrt(dt / s) pi^(-1/4) exp(i w0 eta) exp(-eta^2 / 2).  The Fourier-domain route the
+    oracle (and pycwt) takes is the same quantity up to the sampling of psi^ and the periodic wrap, so
+    away from the edges and for scales resolved by the grid the two agree to round-off (psi^ is
+    effectively band-limited): an anchor for the
+    sign conventions, the sqrt(2 pi s / dt) normalisation and the scale / frequency axes that does not
+    pass through any FFT."""
+    rng = np.random.default_rng(11)
+    n, dt = 512, 0.25
+    x = rng.standard_normal(n).cumsum()
+    x = (x - x.mean()) / x.std()
+    W, sj, *_ = po.cwt(x, dt, 1 / 4, 4 * dt, 16)
+    t = np.arange(n)
+    for j in (2, 6, 10):                                  # s / dt = 5.7, 11.3, 22.6: well resolved, support << n
+        s = sj[j]
+        for m in (200, 256, 300):                         # interior samples
+            eta = (t - m) * dt / s
+            psi = np.sqrt(dt / s) * np.pi ** -0.25 * np.exp(1j * 6.0 * eta) * np.exp(-0.5 * eta ** 2)
+            direct = np.sum(x * np.conj(psi))
+            assert abs(W[j, m] - direct) <= 1e-10 * np.abs(W[j]).max(), (j, m, W[j, m], direct)   # measured 3e-16
+
+
+def test_time_smoothing_matches_the_gaussian_window_definition():
+    """Grinsted et al. (2004) smooth in time with a Gaussian exp(-t^2 / (2 s^2)) normalised to unit
+    weight; pycwt applies it as exp(-0.5 (s/dt)^2 w^2) in the Fourier domain.  Evaluated directly as a
+    time-domain convolution (sigma = s/dt samples, zero beyond the series), the interior of the
+    time-smoothed field must agree to round-off: an FFT-free anchor for Morlet.smooth's first half."""
+    rng = np.random.default_rng(3)
+    n, dt, dj = 400, 1 / 12, 1 / 4
+    field = rng.standard_normal((6, n)) ** 2
+    sj = 2 * dt * 2.0 ** (np.arange(6) * 1.0 + 1)          # s/dt = 4 .. 128
+    m = po.Morlet()
+    # undo the scale boxcar by giving smooth one row at a time with dj large enough for a 1-tap window
+    for i, s in enumerate(sj[:4]):
+        T = m.smooth(field[i:i + 1], dt, 1.2, sj[i:i + 1])     # rect(round(0.6 / 1.2 * 2)) = rect(1): identity
+        sigma = s / dt
+        t = np.arange(n)
+        for c in (n // 2 - 7, n // 2, n // 2 + 31):
+            if c - 8 * sigma < 0 or c + 8 * sigma >= n:
+                continue
+            g = np.exp(-0.5 * ((t - c) / sigma) ** 2) / (sigma * np.sqrt(2 * np.pi))
+            assert abs(T[0, c] - np.sum(field[i] * g)) <= 1e-9 * field[i].max(), (i, c)

@@ -350,11 +350,12 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 // one-sided spectrum Y[k], k < 1024, the output samples t = 2u + q of phase q are
 //   x[2u + q] = sum_{k < 1024} (Y[k] w_N^(q k)) w1024^(k u):
 // two inverse transforms of the same band, the second with a pre-twiddle from a shared-memory
-// table.  Each phase stores its own samples at stride 2 (the two halves of a 128-byte line meet in
-// L2; DRAM traffic is unchanged.  Parking phase 0 in registers to store whole lines costs 50
-// registers and 4 warps: 3-8 % slower below ~1700 samples, 13 % faster at 2048).  The forward transform comes from k_fwd_fft (cwt.cu) as xhat [batch][N]; rows re-read
-// their band through L1 (__ldg), so shared memory holds only the transpose buffer and the tables:
-// 16 warps per SM like the 1024 kernel.
+// table.  Short rows: each phase stores its own samples at stride 2 (the two halves of a 128-byte
+// line meet in L2).  Long rows (STAGE): phase 0 waits in shared memory and phase 1 stores (t, t + 1)
+// pairs, whole lines (see the template's comment for the measured trade).  The forward transform
+// comes from k_fwd_fft (cwt.cu) as xhat [batch][N]; rows re-read their band through L1 (__ldg), so
+// shared memory holds only the transpose buffers, the tables and the stage: 16 warps per SM like
+// the 1024 kernel.
 // The 4-fold version of this for nfft = 4096 (samples 4u + q, bins 1024..2047 folded into each
 // pass) was built and measured at 2.7e11 coeff/s against 4.0e11 for the radix-16 register rows of
 // wct_fast.cu: its stride-4 stores turn every 32-byte sector into four 8-byte L2 write requests

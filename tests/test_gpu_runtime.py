@@ -272,3 +272,34 @@ def test_resident_batch_pipelines_post_processing(shim, series):
     ph = res["phase"].cpu().numpy()
     assert np.allclose(res["phase_diff_u"].cpu().numpy(), np.cos(0.5 * np.pi - ph), atol=1e-15)
     assert np.allclose(res["phase_diff_v"].cpu().numpy(), np.sin(0.5 * np.pi - ph), atol=1e-15)
+
+
+def test_error_behaviour_of_the_runtime_entry_points(shim):
+    """Bad arguments come back as exceptions with the library's message, and leave it usable."""
+    import ctypes as C
+    lib = shim.lib()
+    with pytest.raises((ValueError, shim.WaveletEngineError), match="GPUs requested"):
+        shim.init_multi(99)
+    assert shim.gpu_count() == 1
+    # WTB_DEVICE_PTRS with a host pointer: refused before any kernel is launched
+    x = np.zeros((2, 64), dtype=np.float32)
+    out = np.zeros((2, 9, 64), dtype=np.float32)
+    launches = shim.kernel_launches()
+    rc = lib.wtb_cwt_morlet(x.ctypes.data_as(C.c_void_p), 2, 64, 64, DT, 0.25, 2 * DT, 8, 6.0, shim.DEVICE_PTRS,
+                            out.ctypes.data_as(C.c_void_p), None, None)
+    assert rc == -1 and b"not a device pointer" in lib.wtb_last_error()
+    assert shim.kernel_launches() == launches
+    # the one-call significance takes host buffers only, and a resolved J
+    sig = np.zeros(9)
+    rc = lib.wtb_wct_significance(0.5, 0.5, DT, 0.25, 2 * DT, 8, 6.0, 0.95, 4, C.c_uint64(0), None, shim.DEVICE_PTRS,
+                                  sig.ctypes.data_as(C.POINTER(C.c_double)), None)
+    assert rc == -1 and b"host buffers only" in lib.wtb_last_error()
+    with pytest.raises(ValueError):
+        shim.wct_significance(0.5, 0.5, DT, 0.25, 2 * DT, -1, mc_count=4)
+    with pytest.raises(ValueError):
+        shim.wct_significance(1.5, 0.5, DT, 0.25, 2 * DT, 8, mc_count=4)          # |a1| >= 1
+    with pytest.raises(ValueError):
+        shim.set_fft_padding("mirror")
+    # still usable
+    p, _ = shim.cwt_morlet(np.arange(64.0), DT, 0.25, 2 * DT, 8, f64=True)
+    assert np.isfinite(p).all()

@@ -4,8 +4,10 @@
  *       -Lwavelet_transformer_b200/lib -lwavelet_sm100a -Wl,-rpath,$PWD/wavelet_transformer_b200/lib -lm
  *   /tmp/c_abi_demo            # needs a B200; prints one line of checksums
  *
- * Mirrors src/cwt.py:110-114 (pycwt.cwt + |W|^2 of one series, float64) and src/modwt.py:126
- * (MODWT, LA8, J = 4) on a deterministic test signal.
+ * Mirrors src/cwt.py:110-114 (pycwt.cwt + |W|^2 of one series, float64), src/modwt.py:126
+ * (MODWT, LA8, J = 4) on a deterministic test signal, and the Monte-Carlo coherence significance
+ * that src/wct.py:106-118 reaches through pycwt.wct(sig=True): one call, spread over every GPU
+ * named by WTB_GPUS (wtb_init_multi), thresholds independent of the GPU count.
  */
 #include <math.h>
 #include <stdio.h>
@@ -60,8 +62,19 @@ int main(void) {
   }
   for (int i = 0; i < (JM + 1) * N0; ++i) energy_w += w[i] * w[i];
 
-  printf("S=%d peak_scale=%.6f power_sum=%.9e modwt_energy_ratio=%.12f imodwt_err=%.3e launches=%llu\n", S,
-         scales[smax], psum, energy_w / energy_x, err, (unsigned long long)wtb_kernel_launches());
+  /* 95 % coherence thresholds of two AR(1) processes (0.8, 0.6): 24 realisations, seed 7 */
+  enum { JS = 24 };
+  double sig95[JS + 1];
+  static uint64_t hist[(JS + 1) * WTB_NBINS];
+  CHECK(wtb_init_multi(0)); /* WTB_GPUS, else every visible device; one device needs no workers */
+  CHECK(wtb_wct_significance(0.8, 0.6, dt, 0.25, s0, JS, f0, 0.95, 24, 7, NULL, 0, sig95, hist));
+  unsigned long long hist_total = 0;
+  for (int i = 0; i < (JS + 1) * WTB_NBINS; ++i) hist_total += hist[i];
+
+  printf("S=%d peak_scale=%.6f power_sum=%.9e modwt_energy_ratio=%.12f imodwt_err=%.3e sig95_0=%.9f "
+         "hist_total=%llu gpus=%d launches=%llu\n", S,
+         scales[smax], psum, energy_w / energy_x, err, sig95[0], hist_total, wtb_gpu_count(),
+         (unsigned long long)wtb_kernel_launches());
   free(scales);
   free(power);
   wtb_shutdown();

@@ -218,6 +218,11 @@ def test_c_abi_demo_matches_python(tmp_path):
     w = mo.modwt(x, "sym4", 4)
     assert float(fields["modwt_energy_ratio"]) == pytest.approx((w ** 2).sum() / (x ** 2).sum(), abs=1e-10)
     assert float(fields["imodwt_err"]) < 1e-10 and int(fields["launches"]) >= 4
+    # the one-call Monte-Carlo significance from C equals the Python binding's (same seed, any GPU count)
+    from wavelet_transformer_b200 import _shim
+    sig, hist = _shim.wct_significance(0.8, 0.6, 1 / 12, 0.25, 2 / 12, 24, mc_count=24, seed=7, f64=False, return_hist=True)
+    assert int(fields["hist_total"]) == int(hist.sum()) and float(fields["sig95_0"]) == pytest.approx(sig[0], abs=1e-9)
+    assert int(fields["gpus"]) >= 1
 
 
 def test_transform_helper_builders(series, shim_nogpu):

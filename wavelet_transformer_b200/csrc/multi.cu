@@ -169,14 +169,18 @@ void pool_shutdown() {
 }
 
 int run_sharded(int64_t total, int64_t min_total, cudaStream_t caller_stream, ShardFn fn, void *ctx) {
+  // a pool worker that reaches a sharding entry point runs its block on its own device
+  if (pool_size() < 2 || tl_worker_device >= 0 || total < min_total || total < 2)
+    return fn(ctx, 0, 0, total, caller_stream);
+  // the pool is only read under the call lock: wtb_init_multi / wtb_shutdown take the same lock
+  // before they tear it down
+  std::lock_guard<std::mutex> call(g_call_mu);
   Pool *p = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     p = g_pool;
   }
-  // a pool worker that reaches a sharding entry point runs its block on its own device
-  if (!p || tl_worker_device >= 0 || total < min_total || total < 2) return fn(ctx, 0, 0, total, caller_stream);
-  std::lock_guard<std::mutex> call(g_call_mu);
+  if (!p) return fn(ctx, 0, 0, total, caller_stream);
   const int G = (int)std::min<int64_t>((int64_t)p->w.size(), total);
   for (int r = 0; r < G; ++r) {
     const int64_t first = total * r / G, count = total * (r + 1) / G - first;
@@ -280,19 +284,15 @@ extern "C" int wtb_wct_significance(double a1, double a2, double dt, double dj, 
   mc_row_has_points(nsurr, dt, ax, f0, &any);
   std::vector<uint64_t> hist(cells, 0);
 
-  Pool *p = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    p = g_pool;
-  }
-  const int G = p ? (int)std::min<int64_t>((int64_t)p->w.size(), std::max<int64_t>(mc_count, 1)) : 1;
-  if (!p || G < 2) {
+  const int G = (int)std::min<int64_t>(pool_size(), std::max<int64_t>(mc_count, 1));
+  if (G < 2) {
     WTB_TRY(wtb_wct_mc_hist(a1, a2, dt, dj, s0, J, f0, 0, mc_count, seed, surrogates, flags, hist.data(), nullptr));
   } else if (surrogates) {
     // host-injected series (parity mode): each device takes a block, histograms meet on the host
     std::vector<std::vector<uint64_t>> part(G, std::vector<uint64_t>(cells, 0));
     const size_t pair_bytes = ((flags & WTB_F64) ? 8 : 4) * 2 * (size_t)nsurr;
     const int rc = run_sharded_fn(mc_count, 2, nullptr, [&](int r, int64_t first, int64_t count, cudaStream_t st) {
+      if (r >= G) { set_error("the GPU pool changed during the call"); return WTB_EINVAL; }
       return wtb_wct_mc_hist(a1, a2, dt, dj, s0, J, f0, first, count, seed, (const char *)surrogates + first * pair_bytes,
                              flags, part[r].data(), st);
     });
@@ -300,7 +300,17 @@ extern "C" int wtb_wct_significance(double a1, double a2, double dt, double dj, 
     for (int r = 0; r < G; ++r)
       for (size_t i = 0; i < cells; ++i) hist[i] += part[r][i];
   } else {
-    std::lock_guard<std::mutex> call(g_call_mu);
+    std::lock_guard<std::mutex> call(g_call_mu);      // the pool is only read (and torn down) under this lock
+    Pool *p = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      p = g_pool;
+    }
+    if (!p || (int)p->w.size() < G) {                 // the pool went away between the two looks
+      WTB_TRY(wtb_wct_mc_hist(a1, a2, dt, dj, s0, J, f0, 0, mc_count, seed, nullptr, flags, hist.data(), nullptr));
+      if (hist_out) std::memcpy(hist_out, hist.data(), sizeof(uint64_t) * cells);
+      return wtb_wct_sig_from_hist(hist.data(), S, maxscale, level, any.data(), sig95);
+    }
     // phase 1: every device bins its block of realisations into its own histogram
     for (int r = 0; r < G; ++r) {
       Worker *w = p->w[r].get();

@@ -594,7 +594,7 @@ def main():
     ap.add_argument("--series", type=int, default=125_000, help="series per GPU per step (cfg4 shard)")
     ap.add_argument("--secondary-steps", type=int, default=20)
     ap.add_argument("--e2e-series", type=int, default=8192)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture")

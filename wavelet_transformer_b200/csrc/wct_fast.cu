@@ -181,8 +181,8 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, int S_run, const
         const float xi = fmaf(I[r].x, R[r].y, -R[r].x * I[r].y);
         if (w12) w12[obase + t] = make_float2(xr, xi);
         if (phase) phase[obase + t] = atan2f(xi, xr);
-        pr = make_float2(m2.x * rp.inv_s, xr * rp.inv_s);
-        pi = make_float2(-m2.y * rp.inv_s, -xi * rp.inv_s);
+        pr = mul2(make_float2(m2.x, xr), bc(rp.inv_s));
+        pi = mul2(make_float2(m2.y, xi), bc(-rp.inv_s));
       }
       nR[br4(r)] = pr;
       nI[br4(r)] = pi;
@@ -202,7 +202,8 @@ k_wct_spec_4096(const float2 *__restrict__ xhat, int n0, int S, int S_run, const
     const float k2v = kk * kk;
     if (k2v <= rp.kc2) {
       const float g = ex2(fmaf(rp.gcoef, k2v, -12.0f));
-      srow[bin] = make_float4(R[r].x * g, R[r].y * g, -I[r].x * g, -I[r].y * g);
+      const float2 sr = mul2(R[r], bc(g)), si = mul2(I[r], bc(-g));
+      srow[bin] = make_float4(sr.x, sr.y, si.x, si.y);
     }
   }
 }

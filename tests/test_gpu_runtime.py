@@ -303,3 +303,23 @@ def test_error_behaviour_of_the_runtime_entry_points(shim):
     # still usable
     p, _ = shim.cwt_morlet(np.arange(64.0), DT, 0.25, 2 * DT, 8, f64=True)
     assert np.isfinite(p).all()
+
+
+def test_wtb_gpus_environment_variable_builds_the_pool_at_load():
+    """WTB_GPUS=n is all a Streamlit deployment sets: the pool exists as soon as the library loads."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    code = ("from wavelet_transformer_b200 import _shim, pycwt_compat as w; import numpy as np;"
+            "print(_shim.gpu_count());"
+            "s = w.wct_significance(0.8, 0.6, 1/12, 1/4, 2/12, 24, mc_count=10, cache=False, seed=3);"
+            "print(float(np.nansum(s)))")
+    outs = []
+    for gpus in ("1", "2"):
+        env = dict(os.environ, WTB_GPUS=gpus, WTB_POOL_SHARE_DEVICES="1")
+        proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=env, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        outs.append(proc.stdout.split())
+    assert outs[0][0] == "1" and outs[1][0] == "2"
+    assert outs[0][1] == outs[1][1]          # same thresholds from one and from two pool devices

@@ -24,6 +24,9 @@ bracketed by barrier + synchronize, MAX over ranks; rank 0 prints one JSON line.
 `e2e` of wct_mc is the call a user of the reference makes -- pycwt's wct_significance, here
 `wtb_wct_significance` -- in ONE process that drives all N GPUs through the library's own worker
 pool (rank 0 makes the call, the other ranks wait on a CPU barrier), host wall clock.
+`e2e_host_surrogates` is the same job with a real input payload: the surrogate pairs come from pinned
+HOST memory (north_star's per-realisation parity mode), 2.68 GB of H2D per job, double-buffered
+against the kernels inside the library; it must give the histogram of the device-RNG arm.
 `--impl reference` times the CPU restatement of the reference's path (oracle/, NumPy float64 --
 pycwt itself is not installable offline) on all host cores instead.
 """
@@ -405,6 +408,56 @@ def bench_mc(c, args, sampler):
                "same_numbers_as_value_arm": True}
     c.cpu_barrier()
 
+    # ---- end to end with a real input payload: host-supplied surrogates (north_star's per-realisation
+    # parity mode).  Every rank holds its block of the job's surrogate pairs in pinned host memory;
+    # a step = H2D of the block (double-buffered against the kernels inside the library) + pipeline +
+    # histogram D2H + the all-reduce + percentile on rank 0.
+    e2e_inj = None
+    if not args.no_injected:
+        nloc = stop - first
+        sur_h = torch.empty((nloc, 2, nsurr), dtype=torch.float32).pin_memory()
+        blk = 4096
+        tmp = torch.empty((blk, 2, nsurr), dtype=torch.float32, device=c.dev)
+        for b0 in range(0, nloc, blk):          # the same series the device RNG draws: same histogram expected
+            nb = min(blk, nloc - b0)
+            shim.rednoise_device(MC["a1"], MC["a2"], nsurr, first + b0, nb, MC["seed"], tmp.data_ptr(),
+                                 stream=torch.cuda.current_stream().cuda_stream)
+            sur_h[b0:b0 + nb].copy_(tmp[:nb])
+        torch.cuda.synchronize()
+        del tmp
+        lib = shim.lib()
+        import ctypes as C
+        hist_h = np.zeros((S, shim.NBINS), dtype=np.uint64)
+
+        def inj_step():
+            hist_h[:] = 0
+            rc = lib.wtb_wct_mc_hist(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], MC["f0"], first, nloc,
+                                     C.c_uint64(MC["seed"]), C.c_void_p(sur_h.data_ptr()), 0,
+                                     hist_h.ctypes.data_as(C.c_void_p), None)
+            if rc != 0:
+                raise RuntimeError(lib.wtb_last_error().decode())
+            t = torch.from_numpy(hist_h.view(np.int64)).to(c.dev)
+            engine.reduce_histogram(t)
+            return shim.wct_sig_from_hist(t.cpu().numpy().astype(np.uint64), maxscale, MC["level"], has), t
+        sig_i, t_i = inj_step()
+        if c.rank == 0:
+            assert np.array_equal(t_i.cpu().numpy().astype(np.uint64), total), "injected surrogates give another histogram"
+        c.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            inj_step()
+        torch.cuda.synchronize()
+        inj_s = c.max_over_ranks(time.perf_counter() - t0)
+        e2e_inj = {"value": R * args.e2e_steps / inj_s, "unit": "surrogates/s", "ms_per_step": 1e3 * inj_s / args.e2e_steps,
+                   "h2d_bytes_per_step": 4 * 2 * nsurr * R, "h2d_bytes_per_step_per_rank": 4 * 2 * nsurr * nloc,
+                   "d2h_bytes_per_step": 8 * S * shim.NBINS * c.world, "steps": args.e2e_steps,
+                   "path": "wtb_wct_mc_hist with HOST-supplied surrogates in pinned memory (each rank its block), "
+                           "histogram back to the host, all-reduce, wtb_wct_sig_from_hist; H2D, kernels and D2H inside "
+                           "the timed region",
+                   "same_histogram_as_value_arm": True}
+        del sur_h
+    c.barrier()
+
     ach = MC_FLOP * R / c.world / per_step_s / 1e12      # per GPU: every rank runs R / world realisations
     traffic = _profile_json("r2_traffic_mc.json")
     roofline = {"bound": "fp32", "achieved": ach, "peak": FP32_PEAK_NOMINAL / 1e12, "unit": "TFLOP/s",
@@ -428,6 +481,8 @@ def bench_mc(c, args, sampler):
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "ms_per_step_spread": spread, "allreduce": allreduce, "checks": check,
     }
+    if e2e_inj:
+        line["e2e_host_surrogates"] = e2e_inj
     return line
 
 
@@ -600,6 +655,7 @@ def main():
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-injected", action="store_true", help="skip the host-supplied-surrogates end-to-end arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -129,6 +129,11 @@ int staging_reserve(size_t bytes, void **out);
 // small buffer for kernel parameter tables, separate from the two arenas above so a callee can
 // fill it while its caller's arena holds live data
 int params_reserve(size_t bytes, void **out);
+// An internal copy stream of the calling thread on the current device (created once, destroyed
+// when the thread exits): host-to-device copies of the next chunk run there while the kernels of
+// the current chunk occupy the caller's stream.
+int copy_stream(cudaStream_t *out);
+
 // small page-locked host buffer of the calling thread (results that go back to pageable caller
 // memory bounce through it); grow-only, freed when the thread exits
 int pinned_reserve(size_t bytes, void **out);

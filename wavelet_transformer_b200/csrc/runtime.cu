@@ -252,6 +252,27 @@ static int reserve(int which, size_t bytes, void **out) {
   return WTB_OK;
 }
 
+struct CopyStreams {
+  struct Entry { int device; cudaStream_t s; };
+  std::vector<Entry> entries;
+  ~CopyStreams() {
+    for (Entry &e : entries) cudaStreamDestroy(e.s);
+    cudaGetLastError();
+  }
+};
+static thread_local CopyStreams tl_copy;
+
+int copy_stream(cudaStream_t *out) {
+  for (auto &e : tl_copy.entries)
+    if (e.device == tl_device) { *out = e.s; return WTB_OK; }
+  CopyStreams::Entry e;
+  e.device = tl_device;
+  WTB_CUDA(cudaStreamCreateWithFlags(&e.s, cudaStreamNonBlocking));
+  tl_copy.entries.push_back(e);
+  *out = e.s;
+  return WTB_OK;
+}
+
 struct PinnedBuf {
   void *ptr = nullptr;
   size_t cap = 0;

@@ -21,12 +21,14 @@ Workloads (one "step" = one pass of the hot path over one batch of synthetic inp
 
 Under torchrun every rank drives one GPU; timing is CUDA events on the launching stream,
 bracketed by barrier + synchronize, MAX over ranks; rank 0 prints one JSON line.
-`e2e` of wct_mc is the call a user of the reference makes -- pycwt's wct_significance, here
-`wtb_wct_significance` -- in ONE process that drives all N GPUs through the library's own worker
-pool (rank 0 makes the call, the other ranks wait on a CPU barrier), host wall clock.
-`e2e_host_surrogates` is the same job with a real input payload: the surrogate pairs come from pinned
-HOST memory (north_star's per-realisation parity mode), 2.68 GB of H2D per job, double-buffered
-against the kernels inside the library; it must give the histogram of the device-RNG arm.
+`e2e` of wct_mc is the job through the public API with HOST buffers: the surrogate pairs come from
+pinned host memory (north_star's per-realisation parity mode; each rank its block), 2.68 GB of H2D
+per job, double-buffered against the kernels inside the library, histogram back to the host,
+all-reduce, percentile; it must give the histogram of the device-RNG arm (asserted).
+`e2e_one_call` is the call a user of the reference makes -- pycwt's wct_significance, here
+`wtb_wct_significance`: parameters in, thresholds out, no input payload -- in ONE process that
+drives all N GPUs through the library's own worker pool (rank 0 makes the call, the other ranks
+wait on a CPU barrier), host wall clock.
 `--impl reference` times the CPU restatement of the reference's path (oracle/, NumPy float64 --
 pycwt itself is not installable offline) on all host cores instead.
 """
@@ -478,11 +480,11 @@ def bench_mc(c, args, sampler):
         "metric": "wct_mc_surrogates_per_sec", "value": value, "unit": "surrogates/s", "n_gpus": c.world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": mc_config(args),
-        "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "e2e": e2e_inj if e2e_inj else e2e, "gpu_launches": launches, "clocks": clocks,
         "ms_per_step_spread": spread, "allreduce": allreduce, "checks": check,
     }
     if e2e_inj:
-        line["e2e_host_surrogates"] = e2e_inj
+        line["e2e_one_call"] = e2e      # the reference-facing call (parameters in, thresholds out: no input payload)
     return line
 
 

@@ -429,21 +429,26 @@ def bench_mc(c, args, sampler):
         del tmp
         lib = shim.lib()
         import ctypes as C
-        hist_h = np.zeros((S, shim.NBINS), dtype=np.uint64)
+        hist_pin = torch.zeros((S, shim.NBINS), dtype=torch.int64).pin_memory()     # the call's host histogram
+        hist_h = hist_pin.numpy().view(np.uint64)
+        t_dev = torch.zeros((S, shim.NBINS), dtype=torch.int64, device=c.dev)
 
         def inj_step():
             hist_h[:] = 0
             rc = lib.wtb_wct_mc_hist(MC["a1"], MC["a2"], DT, MC["dj"], MC["s0"], MC["J"], MC["f0"], first, nloc,
                                      C.c_uint64(MC["seed"]), C.c_void_p(sur_h.data_ptr()), 0,
-                                     hist_h.ctypes.data_as(C.c_void_p), None)
+                                     C.c_void_p(hist_pin.data_ptr()), None)
             if rc != 0:
                 raise RuntimeError(lib.wtb_last_error().decode())
-            t = torch.from_numpy(hist_h.view(np.int64)).to(c.dev)
-            engine.reduce_histogram(t)
-            return shim.wct_sig_from_hist(t.cpu().numpy().astype(np.uint64), maxscale, MC["level"], has), t
+            if c.world > 1:                       # the one collective: histograms meet on the devices
+                t_dev.copy_(hist_pin, non_blocking=True)
+                engine.reduce_histogram(t_dev)
+                hist_pin.copy_(t_dev, non_blocking=True)
+                torch.cuda.synchronize()
+            return shim.wct_sig_from_hist(hist_h, maxscale, MC["level"], has), hist_h
         sig_i, t_i = inj_step()
         if c.rank == 0:
-            assert np.array_equal(t_i.cpu().numpy().astype(np.uint64), total), "injected surrogates give another histogram"
+            assert np.array_equal(t_i, total), "injected surrogates give another histogram"
         c.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):

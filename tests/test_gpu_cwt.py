@@ -255,10 +255,11 @@ def test_cwt_fp32_nfft4096_register_rows(shim, n0, batch):
 @pytest.mark.parametrize("n0,dj,J", [(1346, 1 / 12, 84), (1345, 1 / 12, 84), (2048, 1 / 8, 70), (1025, 1 / 4, -1)])
 def test_cwt_fp32_nfft2048_interleaved_passes(shim, monkeypatch, n0, dj, J):
     """Batches of 1025..2048-sample series (BASELINE cfg1's 1346-month CPI shape) take the
-    warp-autonomous 1024-point kernel twice per row (even / odd output samples), even and odd
-    row lengths.  Oracle parity on sampled series, generic-kernel parity on all."""
+    two-warps-per-row kernel (even / odd bins, one 1024-point transform each), even and odd row
+    lengths.  Oracle parity on sampled series, generic-kernel parity on all.  1100 series give
+    every CTA seven or eight series: its three-slot spectrum ring is refilled twice."""
     rng = np.random.default_rng(n0)
-    batch = 300                                   # >= the 128-series threshold of the fast path
+    batch = 1100 if n0 == 1346 else 300
     x = rng.standard_normal((batch, n0)).cumsum(axis=1) * 0.05 + rng.standard_normal((batch, n0))
     power, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False)
     gen, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, generic_only=True)
@@ -266,7 +267,7 @@ def test_cwt_fp32_nfft2048_interleaved_passes(shim, monkeypatch, n0, dj, J):
     for b in range(batch):
         ok, err = normwise_close(power[b], gen[b], 1e-4)
         assert ok, f"series {b}: {err:.3e} vs the generic kernel"
-    for b in (0, 147, 148, 299):
+    for b in (0, 147, 148, batch - 1):
         ref = np.abs(_oracle_plane(x[b], DT, dj, 2 * DT, J)) ** 2
         ok, err = normwise_close(power[b], ref, 1e-4)
         assert ok, f"series {b}: {err:.3e} vs the oracle"

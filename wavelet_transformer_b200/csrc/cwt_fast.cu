@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "fft32_gen.cuh"
+#include "filterbank_common.cuh"
 
 namespace wtb {
 
@@ -586,6 +587,282 @@ k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
   }
 }
 
+
+// ---- nfft = 2048, two warps per scale row (k_cwt_pair_2048) ---------------------------------------
+// Decimation in frequency instead of in time: with E[u], G[u] the 1024-point inverse transforms of the
+// even and of the odd bins of the one-sided spectrum Y[k], k < 1024,
+//   x[u]        = E[u] + w2048^u G[u]
+//   x[u + 1024] = E[u] - w2048^u G[u],          u < 1024.
+// Warp h of a pair owns the bins of parity h (512 of them: step A of its 1024-point transform has at
+// most 16 non-zero inputs, one butterfly stage less than the time-decimated passes above, and a row
+// is single-pass up to k_hi < 64 instead of 32), the odd warp multiplies by w2048^u, and the two
+// exchange half of their outputs through a 4 KB mailbox: warp 0 finishes u < 512, warp 1 u >= 512,
+// each storing whole 128-byte lines of x[u] and x[u + 1024] -- no strided stores, no staging, and no
+// transform of samples past n0 is combined or stored.
+// The seven pairs of a CTA work on ONE series: its spectrum X^ (8 KB) arrives by a TMA bulk copy into a
+// ring of three slots (mbarrier full / done), so no row ever re-reads global memory, and the pairs
+// draw rows from a shared counter (small scales first, they are the expensive ones).
+constexpr int kPairWarps = 16;
+constexpr int kPairs = kPairWarps / 2;
+constexpr int kRing = 3;
+
+struct alignas(16) WarpSmemP {
+  float trr[32 * kTrStride];        // transpose buffer; its first 32 floats double as Y[k] of a single-pass row,
+  float tri[32 * kTrStride];        // its first 2 KB as the mailbox the partner warp fills (8 positions x 32 lanes x 8 B)
+};
+
+struct CtaSmemP {
+  float4 tw_a[16][32];              // as in CtaSmem: twiddles of the 1024-point transform
+  float4 tw_b[16][32];
+  float4 tw_o[16][32];              // (c, -s, s, c) of w2048^(lane + 32 p): the pair (u, u + 512) of the odd half
+  float2 xh[kRing][kN];             // X^[k], k < 1024, of the series in flight
+  RowParam row[kMaxRowsF];
+  ushort2 coi[kMaxRowsF];
+  uint64_t full[kRing];             // TMA completion of a slot
+  uint64_t done[kRing];             // every pair has finished the slot's series
+  int next_row[kRing];
+  int pair_row[2][kPairs];          // row drawn by the pair's leader, by series parity (the partner may still be
+                                    // reading the last draw of one series when the leader draws for the next)
+  WarpSmemP w[kPairWarps];
+};
+static_assert(sizeof(CtaSmemP) <= 227 * 1024, "the pair kernel's tables, ring and per-warp buffers must fit one CTA");
+
+__device__ __forceinline__ void pair_sync(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+template <bool COI>
+__global__ void __launch_bounds__(kPairWarps * 32, 1)
+k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
+                const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
+                float *__restrict__ power, int split) {
+  constexpr int kNF = 2 * kN;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaSmemP &sm = *reinterpret_cast<CtaSmemP *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int pair = warp >> 1, h = warp & 1;
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int p = i >> 5, l = i & 31;
+    float s0, c0, s1, c1;
+    sincospif(2.0f * (float)(p * l) / (float)kN, &s0, &c0);
+    sincospif(2.0f * (float)((p + 16) * l) / (float)kN, &s1, &c1);
+    sm.tw_a[p][l] = make_float4(c0, c1, s0, s1);
+    sincospif(2.0f * (float)(2 * p * l) / (float)kN, &s0, &c0);
+    sincospif(2.0f * (float)((2 * p + 1) * l) / (float)kN, &s1, &c1);
+    sm.tw_b[p][l] = make_float4(c0, c1, s0, s1);
+    sincospif(2.0f * (float)(l + 32 * p) / (float)kNF, &s0, &c0);      // w2048^(u + 512) = i w2048^u
+    sm.tw_o[p][l] = make_float4(c0, -s0, s0, c0);
+  }
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    sm.row[i] = rows[i];
+    if (COI) sm.coi[i] = coi[i];
+  }
+  const int64_t items = batch * split;            // one CTA item = one series and every split-th row from row c on
+  int next_load = 0;                              // thread 0: local index of the next series to fetch
+  auto issue_load = [&](int j) {
+    const int64_t it = blockIdx.x + (int64_t)j * gridDim.x;
+    const int slot = j % kRing;
+    sm.next_row[slot] = 0;
+    mbar_expect_tx(&sm.full[slot], (uint32_t)(sizeof(float2) * kN));
+    tma_load_1d(&sm.xh[slot][0], xhat + (it / split) * kNF, (uint32_t)(sizeof(float2) * kN), &sm.full[slot]);
+  };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&sm.full[i], 1);
+      mbar_init(&sm.done[i], kPairs);
+    }
+    mbar_init_fence();
+    for (; next_load < kRing && blockIdx.x + (int64_t)next_load * gridDim.x < items; ++next_load) issue_load(next_load);
+  }
+  __syncthreads();
+  // refill every slot whose series all pairs have left (thread 0, between rows: never blocks)
+  auto refill = [&](bool block) {
+    while (blockIdx.x + (int64_t)next_load * gridDim.x < items) {
+      const int slot = next_load % kRing;
+      const uint32_t ph = (uint32_t)((next_load / kRing - 1) & 1);
+      if (block) mbar_wait(&sm.done[slot], ph);
+      else if (!mbar_test(&sm.done[slot], ph)) break;
+      issue_load(next_load);
+      ++next_load;
+      block = false;
+    }
+  };
+  WarpSmemP &ws = sm.w[warp];
+  float *const yr = ws.trr, *const yi = ws.tri;
+  float2 *const my_mr = reinterpret_cast<float2 *>(ws.trr), *const my_mi = reinterpret_cast<float2 *>(ws.tri);
+  float2 *const wp_mr = reinterpret_cast<float2 *>(sm.w[warp ^ 1].trr), *const wp_mi = reinterpret_cast<float2 *>(sm.w[warp ^ 1].tri);
+  const float kf = (float)(2 * lane + h);           // this lane's first bin
+  const int tidx = 2 * (lane & 15) + (lane >> 4);
+  const bool leader = (h == 0 && lane == 0);
+  float2 R[16], I[16];
+
+  for (int i = 0;; ++i) {
+    const int64_t it = blockIdx.x + (int64_t)i * gridDim.x;
+    if (it >= items) break;
+    const int slot = i % kRing;
+    const int64_t b = it / split;
+    const int c = (int)(it - b * split);
+    const int nrows = (S - c + split - 1) / split;
+    if (threadIdx.x == 0 && next_load <= i) refill(true);     // only when the pairs ran a whole ring apart
+    mbar_wait(&sm.full[slot], (uint32_t)((i / kRing) & 1));
+    const float2 *xs = &sm.xh[slot][2 * lane + h];
+    volatile int *const my_row = &sm.pair_row[i & 1][pair];
+    if (leader) *my_row = atomicAdd(&sm.next_row[slot], 1);
+    __syncwarp();
+    pair_sync(pair);
+#pragma unroll 1
+    for (;;) {
+      const int r = *my_row;
+      if (r >= nrows) break;
+      const int s = c + split * r;
+      const RowParam rp = sm.row[s];
+      const int L = rp.L, two_pass = rp.multi;
+      const float zl = fmaf(rp.a, kf, -f0);         // s*w_k - f0 at k = 2 lane + h
+      if (two_pass) {
+        // Y[2 (lane + 32 k2) + h] = X^ * daughter for k2 < 2^L <= 16, two k2 per packed op
+        const int M = 1 << (rp.L - 1);
+        const float2 zl2 = make_float2(zl, fmaf(rp.a, 64.0f, zl));
+        const float2 a128 = bc(rp.a * 128.0f);
+        const float2 ln2 = bc(rp.lognorm);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          if (M > below_pow2(m)) {
+            const float2 z = fma2(a128, bc((float)m), zl2);
+            const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);
+            const float2 d = make_float2(ex2(e.x), ex2(e.y));
+            const float2 v0 = xs[128 * m], v1 = xs[128 * m + 64];
+            R[br4(m)] = mul2(make_float2(v0.x, v1.x), d);
+            I[br4(m)] = mul2(make_float2(v0.y, v1.y), d);
+          }
+        }
+      } else {
+        const float d = ex2(fmaf(zl * zl, -0.72134752044f, rp.lognorm));
+        const float2 v0 = xs[0];
+        yr[lane] = v0.x * d;
+        yi[lane] = v0.y * d;
+        __syncwarp();
+        const int M = 1 << (rp.L - 1);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          if (M > below_pow2_16(m)) {
+            const float2 y_r = *reinterpret_cast<const float2 *>(&yr[2 * m]);
+            const float2 y_i = *reinterpret_cast<const float2 *>(&yi[2 * m]);
+            const float4 t = sm.tw_b[m][lane];
+            const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
+            R[br4(m)] = fma2(y_i, neg2(twi), mul2(y_r, twr));
+            I[br4(m)] = fma2(y_r, twi, mul2(y_i, twr));
+          }
+        }
+        __syncwarp();
+      }
+      fft32::dit32(R, I, L);
+      if (two_pass) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const float4 t = sm.tw_a[p][lane];
+          const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
+          const float2 vr = fma2(I[p], neg2(twi), mul2(R[p], twr));
+          const float2 vi = fma2(R[p], twi, mul2(I[p], twr));
+          *reinterpret_cast<float2 *>(&ws.trr[lane * kTrStride + 2 * p]) = vr;
+          *reinterpret_cast<float2 *>(&ws.tri[lane * kTrStride + 2 * p]) = vi;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          R[br4(m)] = make_float2(ws.trr[(2 * m) * kTrStride + tidx], ws.trr[(2 * m + 1) * kTrStride + tidx]);
+          I[br4(m)] = make_float2(ws.tri[(2 * m) * kTrStride + tidx], ws.tri[(2 * m + 1) * kTrStride + tidx]);
+        }
+        __syncwarp();
+        fft32::dit32(R, I, 5);
+      }
+      // position p holds u = lane + 32 p (.x) and u + 512 (.y) of this warp's 1024-point transform
+      if (h) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const float4 t = sm.tw_o[p][lane];
+          const float2 ta = make_float2(t.x, t.y), tb = make_float2(t.z, t.w);
+          const float2 vr = fma2(I[p], neg2(tb), mul2(R[p], ta));
+          I[p] = fma2(R[p], tb, mul2(I[p], ta));
+          R[p] = vr;
+        }
+      }
+      // The mailboxes live in the transpose buffers: both warps must be past their step-B loads
+      __syncwarp();
+      pair_sync(pair);
+      if (h) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {               // warp 0 finishes positions p < 8
+          wp_mr[p * 32 + lane] = R[p];
+          wp_mi[p * 32 + lane] = I[p];
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {               // warp 1 finishes positions p >= 8
+          wp_mr[p * 32 + lane] = R[p + 8];
+          wp_mi[p * 32 + lane] = I[p + 8];
+        }
+      }
+      if (leader) {
+        *my_row = atomicAdd(&sm.next_row[slot], 1);
+        if (threadIdx.x == 0) refill(false);
+      }
+      __syncwarp();
+      pair_sync(pair);
+      const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
+      const int t0 = lane + 256 * h;
+      float *orow = power + (b * S + s) * (int64_t)n0 + t0;
+      // e = even-bin transform, o = twiddled odd-bin transform, both at u = t0 + 32 p (.x) and u + 512 (.y):
+      // x[u] = e + o, x[u + 1024] = e - o -> four whole lines per position
+      auto finish = [&](const int p, const float2 er, const float2 ei, const float2 orr, const float2 oi) {
+        const float2 lr = add2(er, orr), li = add2(ei, oi);
+        float2 lo = fma2(lr, lr, mul2(li, li));      // |x[u]|^2, |x[u + 512]|^2
+        const int ta = t0 + 32 * p;
+        if (COI) {
+          if (ta < tlo || ta > thi) lo.x = NAN;
+          if (ta + 512 < tlo || ta + 512 > thi) lo.y = NAN;
+        }
+        __stcs(orow + 32 * p, lo.x);                 // n0 > 1024: the first half is always inside the row
+        __stcs(orow + 32 * p + 512, lo.y);
+        if (kN + 256 * h + 32 * p < n0) {            // warp-uniform: some lane still has a sample in the second half
+          const float2 hr = fma2(orr, bc(-1.0f), er), hi = fma2(oi, bc(-1.0f), ei);
+          float2 hp = fma2(hr, hr, mul2(hi, hi));    // |x[u + 1024]|^2, |x[u + 1536]|^2
+          if (COI) {
+            if (ta + 1024 < tlo || ta + 1024 > thi) hp.x = NAN;
+            if (ta + 1536 < tlo || ta + 1536 > thi) hp.y = NAN;
+          }
+          if (ta + 1024 < n0) __stcs(orow + 32 * p + 1024, hp.x);
+          if (ta + 1536 < n0) __stcs(orow + 32 * p + 1536, hp.y);
+        }
+      };
+      if (h) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) finish(p, my_mr[p * 32 + lane], my_mi[p * 32 + lane], R[p + 8], I[p + 8]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) finish(p, R[p], I[p], my_mr[p * 32 + lane], my_mi[p * 32 + lane]);
+      }
+    }
+    if (leader) mbar_arrive(&sm.done[slot]);
+  }
+}
+
 }  // namespace
 
 // Per-row sample interval inside the cone of influence, evaluated in double with the expression
@@ -714,6 +991,9 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   // per series for the generic kernel -- measured crossover at about 12 series.
   if (nfft != 2 * kN || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF)) return 1;
   const bool coi = flags & WTB_COI_MASK;
+  // the pair kernel stores the first 1024 samples of a row unconditionally
+  static const bool use_fold_env = std::getenv("WTB_CWT_FOLD") != nullptr;   // the time-decimated kernel, kept for A/B runs
+  const bool use_fold = use_fold_env || n0 <= kN;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;
@@ -722,8 +1002,15 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
     RowParam &r = rows[s];
     r.a = (float)a;
     r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / nfft);
-    r.multi = khi >= 32;
-    r.L = r.multi ? std::max(1, std::min(5, ilog2(khi / 32 + 1))) : ilog2(khi + 1);
+    if (use_fold) {
+      r.multi = khi >= 32;
+      r.L = r.multi ? std::max(1, std::min(5, ilog2(khi / 32 + 1))) : ilog2(khi + 1);
+    } else {
+      // pair kernel: a warp transforms the bins of one parity, j = k / 2 <= jhi < 512
+      const int jhi = khi / 2;
+      r.multi = jhi >= 32;
+      r.L = r.multi ? std::max(1, std::min(4, ilog2(jhi / 32 + 1))) : std::max(1, ilog2(jhi + 1));
+    }
   }
   // the caller's arena holds xhat: row parameters go to the per-thread parameter buffer
   void *prm = nullptr;
@@ -737,6 +1024,18 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
     coi_row_ranges(n0, dt, ax, f0, &rng);
     d_coi = (ushort2 *)(d_rows + kMaxRowsF);
     WTB_CUDA(cudaMemcpyAsync(d_coi, rng.data(), sizeof(ushort2) * S, cudaMemcpyHostToDevice, st));
+  }
+  if (!use_fold) {
+    // fewer series than SMs: the rows of a series are dealt to up to 16 CTAs
+    const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), (int64_t)sm_count() / batch));
+    const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
+    auto run = [&](auto kern) -> int {
+      WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmemP)));
+      kern<<<grid, kPairWarps * 32, sizeof(CtaSmemP), st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
+      WTB_LAUNCH_CHECK();
+      return WTB_OK;
+    };
+    return coi ? run(k_cwt_pair_2048<true>) : run(k_cwt_pair_2048<false>);
   }
   const int64_t machine_warps = (int64_t)sm_count() * kWarpsDefault;
   const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), machine_warps / batch));

@@ -15,12 +15,37 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, cudaStream_t st);
 
+// implemented in cwt_fast.cu: the shape runs the two-warps-per-row kernel, which reads the spectra in pair layout
+bool cwt_pair2048_covers(int64_t batch, int n0, int nfft, int S, double f0);
+
 // implemented in wct_fast.cu (register-FFT rows for nfft = 4096); returns 1 when not covered
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, float2 *d_coef, cudaStream_t st);
 
 // implemented in wct_fast.cu: forward FFTs with the radix-16 register kernel (FP32, N = 4096); 1 = not covered
 int fwd_fft_4096_try(const float *d_y, int64_t nseries, int n0, int N, float2 *d_xhat, cudaStream_t st);
+
+// Forward FFT (N = 2048, FP32) for k_cwt_pair_2048: the positive half of the spectrum leaves in the layout
+// that kernel's warps load with one 16-byte access per packed pair -- per series 8 KB at the start of its
+// xhat row: float4 [parity h][m < 8][lane] = (Re X^[k0], Re X^[k1], Im X^[k0], Im X^[k1]),
+// k0 = 2 (lane + 64 m) + h, k1 = k0 + 64.
+__global__ void k_fwd_fft_pair2048(const float *__restrict__ x, int n0, FftPlan<float> plan, float2 *__restrict__ xhat) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *a = reinterpret_cast<float2 *>(smem_raw);
+  float2 *b = a + plan.M;
+  const int N = plan.n;
+  const int64_t row = blockIdx.x;
+  const float *xr = x + row * n0;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) a[t] = make_float2(t < n0 ? xr[t] : 0.0f, 0.0f);
+  __syncthreads();
+  const float2 *r = plan_fft<float, -1>(a, b, plan);
+  float4 *o = reinterpret_cast<float4 *>(xhat + row * N);
+  for (int i = threadIdx.x; i < 2 * 8 * 32; i += blockDim.x) {
+    const int lane = i & 31, m = (i >> 5) & 7, h = i >> 8;
+    const float2 v0 = r[2 * (lane + 64 * m) + h], v1 = r[2 * (lane + 64 * m) + h + 64];
+    o[i] = make_float4(v0.x, v1.x, v0.y, v1.y);
+  }
+}
 
 // One CTA = one (series, chunk of scales).  smem: 2 * N complex.
 template <typename T>
@@ -119,7 +144,17 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
       fwd_rc = fwd_fft_4096_try((const float *)d_x, batch, n0, N, (float2 *)d_xhat, st);
     if (fwd_rc < 0) return fwd_rc;
   }
-  if (fwd_rc == 1) {
+  bool pair_layout = false;
+  if constexpr (sizeof(T) == 4) {
+    pair_layout = fwd_rc == 1 && mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef &&
+                  cwt_pair2048_covers(batch, n0, N, S, f0);
+    if (pair_layout) {
+      WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft_pair2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_fwd_fft_pair2048<<<(unsigned)batch, threads, smem, st>>>((const float *)d_x, n0, plan, (float2 *)d_xhat);
+      WTB_LAUNCH_CHECK();
+    }
+  }
+  if (fwd_rc == 1 && !pair_layout) {
     k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, plan, d_xhat);
     WTB_LAUNCH_CHECK();
   }

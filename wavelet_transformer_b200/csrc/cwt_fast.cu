@@ -615,7 +615,8 @@ struct CtaSmemP {
   float4 tw_a[16][32];              // as in CtaSmem: twiddles of the 1024-point transform
   float4 tw_b[16][32];
   float4 tw_o[16][32];              // (c, -s, s, c) of w2048^(lane + 32 p): the pair (u, u + 512) of the odd half
-  float2 xh[kRing][kN];             // X^[k], k < 1024, of the series in flight
+  float4 xh[kRing][2][8][32];       // X^ of the series in flight in pair layout (k_fwd_fft_pair2048): [parity h][m][lane] =
+                                    // (Re X^[k0], Re X^[k1], Im X^[k0], Im X^[k1]), k0 = 2 (lane + 64 m) + h, k1 = k0 + 64
   RowParam row[kMaxRowsF];
   ushort2 coi[kMaxRowsF];
   uint64_t full[kRing];             // TMA completion of a slot
@@ -674,14 +675,14 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     sm.row[i] = rows[i];
     if (COI) sm.coi[i] = coi[i];
   }
-  const int64_t items = batch * split;            // one CTA item = one series and every split-th row from row c on
+  const unsigned items = (unsigned)(batch * split);   // one CTA item = one series and every split-th row from row c on (host: < 2^31)
   int next_load = 0;                              // thread 0: local index of the next series to fetch
   auto issue_load = [&](int j) {
-    const int64_t it = blockIdx.x + (int64_t)j * gridDim.x;
+    const unsigned it = blockIdx.x + (unsigned)j * gridDim.x;
     const int slot = j % kRing;
     sm.next_row[slot] = 0;
     mbar_expect_tx(&sm.full[slot], (uint32_t)(sizeof(float2) * kN));
-    tma_load_1d(&sm.xh[slot][0], xhat + (it / split) * kNF, (uint32_t)(sizeof(float2) * kN), &sm.full[slot]);
+    tma_load_1d(&sm.xh[slot][0][0][0], xhat + (int64_t)(it / (unsigned)split) * kNF, (uint32_t)(sizeof(float2) * kN), &sm.full[slot]);
   };
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) {
@@ -689,12 +690,12 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       mbar_init(&sm.done[i], kPairs);
     }
     mbar_init_fence();
-    for (; next_load < kRing && blockIdx.x + (int64_t)next_load * gridDim.x < items; ++next_load) issue_load(next_load);
+    for (; next_load < kRing && blockIdx.x + (unsigned)next_load * gridDim.x < items; ++next_load) issue_load(next_load);
   }
   __syncthreads();
   // refill every slot whose series all pairs have left (thread 0, between rows: never blocks)
   auto refill = [&](bool block) {
-    while (blockIdx.x + (int64_t)next_load * gridDim.x < items) {
+    while (blockIdx.x + (unsigned)next_load * gridDim.x < items) {
       const int slot = next_load % kRing;
       const uint32_t ph = (uint32_t)((next_load / kRing - 1) & 1);
       if (block) mbar_wait(&sm.done[slot], ph);
@@ -714,15 +715,15 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
   float2 R[16], I[16];
 
   for (int i = 0;; ++i) {
-    const int64_t it = blockIdx.x + (int64_t)i * gridDim.x;
+    const unsigned it = blockIdx.x + (unsigned)i * gridDim.x;
     if (it >= items) break;
     const int slot = i % kRing;
-    const int64_t b = it / split;
-    const int c = (int)(it - b * split);
+    const unsigned b = it / (unsigned)split;
+    const int c = (int)(it - b * (unsigned)split);
     const int nrows = (S - c + split - 1) / split;
     if (threadIdx.x == 0 && next_load <= i) refill(true);     // only when the pairs ran a whole ring apart
     mbar_wait(&sm.full[slot], (uint32_t)((i / kRing) & 1));
-    const float2 *xs = &sm.xh[slot][2 * lane + h];
+    const float4 *xs = &sm.xh[slot][h][0][lane];
     volatile int *const my_row = &sm.pair_row[i & 1][pair];
     if (leader) *my_row = atomicAdd(&sm.next_row[slot], 1);
     __syncwarp();
@@ -747,32 +748,51 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
             const float2 z = fma2(a128, bc((float)m), zl2);
             const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);
             const float2 d = make_float2(ex2(e.x), ex2(e.y));
-            const float2 v0 = xs[128 * m], v1 = xs[128 * m + 64];
-            R[br4(m)] = mul2(make_float2(v0.x, v1.x), d);
-            I[br4(m)] = mul2(make_float2(v0.y, v1.y), d);
+            const float4 v = xs[32 * m];
+            R[br4(m)] = mul2(make_float2(v.x, v.y), d);
+            I[br4(m)] = mul2(make_float2(v.z, v.w), d);
           }
         }
       } else {
         const float d = ex2(fmaf(zl * zl, -0.72134752044f, rp.lognorm));
-        const float2 v0 = xs[0];
+        const float4 v0 = xs[0];
         yr[lane] = v0.x * d;
-        yi[lane] = v0.y * d;
+        yi[lane] = v0.z * d;
         __syncwarp();
-        const int M = 1 << (rp.L - 1);
+        // u[j] = Y[j] * w1024^(j * lane) for j < 2^L, two j per packed op; nested warp-uniform branches,
+        // not per-element predicates (a narrow row must not issue the whole unrolled loop)
+        auto pre = [&](const int m) {
+          const float2 y_r = *reinterpret_cast<const float2 *>(&yr[2 * m]);
+          const float2 y_i = *reinterpret_cast<const float2 *>(&yi[2 * m]);
+          const float4 t = sm.tw_b[m][lane];
+          const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
+          R[br4(m)] = fma2(y_i, neg2(twi), mul2(y_r, twr));
+          I[br4(m)] = fma2(y_r, twi, mul2(y_i, twr));
+        };
+        pre(0);
+        if (L >= 2) {
+          pre(1);
+          if (L >= 3) {
+            pre(2); pre(3);
+            if (L >= 4) {
+              pre(4); pre(5); pre(6); pre(7);
+              if (L >= 5) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          if (M > below_pow2_16(m)) {
-            const float2 y_r = *reinterpret_cast<const float2 *>(&yr[2 * m]);
-            const float2 y_i = *reinterpret_cast<const float2 *>(&yi[2 * m]);
-            const float4 t = sm.tw_b[m][lane];
-            const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
-            R[br4(m)] = fma2(y_i, neg2(twi), mul2(y_r, twr));
-            I[br4(m)] = fma2(y_r, twi, mul2(y_i, twr));
+                for (int m = 8; m < 16; ++m) pre(m);
+              }
+            }
           }
         }
         __syncwarp();
       }
-      fft32::dit32(R, I, L);
+      if (L == 1) {
+        // two non-zero inputs: out[t] = in0 + w32^t in1, straight from the definition (no replication
+        // of registers, no scalar last stage)
+        fft32::dft32_two_inputs(R, I);
+      } else {
+        __builtin_assume(L >= 2 && L <= 5);        // RowParam::L of this kernel: no single-input path
+        fft32::dit32(R, I, L);
+      }
       if (two_pass) {
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
@@ -827,7 +847,7 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       pair_sync(pair);
       const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
       const int t0 = lane + 256 * h;
-      float *orow = power + (b * S + s) * (int64_t)n0 + t0;
+      float *orow = power + ((int64_t)b * S + s) * (int64_t)n0 + t0;
       // e = even-bin transform, o = twiddled odd-bin transform, both at u = t0 + 32 p (.x) and u + 512 (.y):
       // x[u] = e + o, x[u + 1024] = e - o -> four whole lines per position
       auto finish = [&](const int p, const float2 er, const float2 ei, const float2 orr, const float2 oi) {
@@ -983,6 +1003,13 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 
 // FP32 CWT + power rows for nfft = 2048 from forward spectra xhat [batch, nfft] (cwt.cu tries
 // this after its forward-FFT kernel).  Returns 1 when the shape is not covered.
+// true: cwt_fast_fold_try runs the two-warps-per-row kernel for this shape and wants the forward
+// spectra in its layout (CtaSmemP::xh; written by k_fwd_fft_pair2048 in cwt.cu)
+bool cwt_pair2048_covers(int64_t batch, int n0, int nfft, int S, double f0) {
+  static const bool use_fold_env = std::getenv("WTB_CWT_FOLD") != nullptr;   // the time-decimated kernel, kept for A/B runs
+  return nfft == 2 * kN && f0 >= kZCut && S <= kMaxRowsF && batch >= min_fast_batch(kMinBatchF) && n0 > kN && !use_fold_env;
+}
+
 int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
@@ -991,9 +1018,8 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
   // per series for the generic kernel -- measured crossover at about 12 series.
   if (nfft != 2 * kN || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF)) return 1;
   const bool coi = flags & WTB_COI_MASK;
-  // the pair kernel stores the first 1024 samples of a row unconditionally
-  static const bool use_fold_env = std::getenv("WTB_CWT_FOLD") != nullptr;   // the time-decimated kernel, kept for A/B runs
-  const bool use_fold = use_fold_env || n0 <= kN;
+  // the pair kernel stores the first 1024 samples of a row unconditionally (n0 > 1024)
+  const bool use_fold = !cwt_pair2048_covers(batch, n0, nfft, S, f0);
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;
@@ -1029,6 +1055,7 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
     // fewer series than SMs: the rows of a series are dealt to up to 16 CTAs
     const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), (int64_t)sm_count() / batch));
     const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
+    WTB_REQUIRE(batch * split < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
     auto run = [&](auto kern) -> int {
       WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmemP)));
       kern<<<grid, kPairWarps * 32, sizeof(CtaSmemP), st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);

@@ -106,7 +106,7 @@ def test_cwt_coi_mask(shim):
 @pytest.mark.parametrize("n0,batch", [(400, 5), (512, 4), (700, 3), (1024, 3), (1346, 13), (2048, 12), (3351, 3), (4096, 2)])
 def test_cwt_coi_mask_fused_fast_kernels(shim, n0, batch):
     """north_star (1): the cone-of-influence mask is fused into the FP32 fast kernels' store loops
-    (nfft 512 two-series, 1024, 2048 fold, 4096 rows).  Inside the cone the power is bit-equal to
+    (nfft 512 two-series, 1024, 2048 warp pairs, 4096 rows).  Inside the cone the power is bit-equal to
     the unmasked fast kernel, outside it is NaN, and the mask itself equals the oracle's
     `period > coi` (the generic kernel's, too)."""
     x = np.random.default_rng(n0).standard_normal((batch, n0))

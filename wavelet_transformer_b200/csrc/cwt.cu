@@ -11,8 +11,8 @@ namespace wtb {
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
                  double f0, int flags, float *d_power, cudaStream_t st);
 
-// implemented in cwt_fast.cu (two interleaved 1024-point passes per row for nfft = 2048); 1 = not covered
-int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
+// implemented in cwt_fast.cu (two warps per row for nfft = 2048, spectra in pair layout); 1 = not covered
+int cwt_pair2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
                       int flags, float *d_power, cudaStream_t st);
 
 // implemented in cwt_fast.cu: the shape runs the two-warps-per-row kernel, which reads the spectra in pair layout
@@ -159,8 +159,8 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
     WTB_LAUNCH_CHECK();
   }
   if constexpr (sizeof(T) == 4) {
-    if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef) {
-      const int rc = cwt_fast_fold_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
+    if (pair_layout) {
+      const int rc = cwt_pair2048_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
       if (rc != 1) return rc;
     }
     if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY)) {

@@ -347,261 +347,26 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 
 
 // ---- nfft = 2048 (series of 1025..2048 samples, e.g. the reference's 1346-month CPI series) ----
-// The same warp-autonomous 1024-point machinery run twice per scale row.  With N = 2 * 1024 and a
-// one-sided spectrum Y[k], k < 1024, the output samples t = 2u + q of phase q are
-//   x[2u + q] = sum_{k < 1024} (Y[k] w_N^(q k)) w1024^(k u):
-// two inverse transforms of the same band, the second with a pre-twiddle from a shared-memory
-// table.  Short rows: each phase stores its own samples at stride 2 (the two halves of a 128-byte
-// line meet in L2).  Long rows (STAGE): phase 0 waits in shared memory and phase 1 stores (t, t + 1)
-// pairs, whole lines (see the template's comment for the measured trade).  The forward transform
-// comes from k_fwd_fft (cwt.cu) as xhat [batch][N]; rows re-read their band through L1 (__ldg), so
-// shared memory holds only the transpose buffers, the tables and the stage: 16 warps per SM like
-// the 1024 kernel.
-// The 4-fold version of this for nfft = 4096 (samples 4u + q, bins 1024..2047 folded into each
-// pass) was built and measured at 2.7e11 coeff/s against 4.0e11 for the radix-16 register rows of
-// wct_fast.cu: its stride-4 stores turn every 32-byte sector into four 8-byte L2 write requests
-// and the L2 request rate becomes the limit.  It was dropped.
-constexpr int kMaxRowsF = 128;
-constexpr int kMinBatchF = 12;
-constexpr int kStageMinN0 = 1888;   // rows longer than this take the staged-store variant (see k_cwt_fast_fold)
-
-template <bool STAGE> struct WarpSmemF {
-  float trr[32 * kTrStride];        // transpose buffer; its first 32 floats double as Y[k] of a single-pass row
-  float tri[32 * kTrStride];
-  float2 stage[STAGE ? 16 : 1][32]; // STAGE: phase 0 of the current row, |w|^2 at t = 2u, (u, u + 512) per lane and p
-};
-
-template <int D, bool STAGE> struct CtaSmemF {
-  float4 tw_a[16][32];              // as in CtaSmem: twiddles of the 1024-point transform
-  float4 tw_b[16][32];
-  float4 tw_c[D - 1][16][32];       // exp(+2*pi*i*q*k/N) for the pair k = lane + 64 m, k + 32, q = 1 .. D-1
-  RowParam row[kMaxRowsF];
-  ushort2 coi[kMaxRowsF];           // COI only (see k_cwt_fast_1024)
-  WarpSmemF<STAGE> w[kWarpsDefault];
-};
-
-// X^ is the only data a warp reads more than once: keep it in L1 ahead of everything else
-__device__ __forceinline__ float2 ldg_keep(const float2 *p) {
-  float2 v;
-  asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-// ... and the power plane is never read back: do not let it displace X^
-__device__ __forceinline__ void st_stream(float *p, float v) {
-  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-
-__device__ __forceinline__ void st_stream2(float *p, float2 v) {
-  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-
-__device__ __forceinline__ constexpr int below_pow2_16(int m) {
-  return m < 8 ? below_pow2(m) : 8;
-}
-
-// STAGE: phase 0 waits in shared memory and whole (t, t + 1) pairs are stored -- DRAM traffic drops
-// from 1.14x to 0.99x of the algorithmic bytes and the re-reads disappear (ncu, profiles/), but
-// the staging costs 32 shared-memory instructions per row and 64 KB of L1 (the X^ re-reads then
-// miss it), so it only pays for long rows (n0 > kStageMinN0: measured 6.2 ms flat per 20 000
-// series against 3.3 ms + 1.6 ms * n0 / 1024 without it).
-template <int D, bool COI, bool STAGE>
-__global__ void __launch_bounds__(kWarpsDefault * 32, 1)
-k_cwt_fast_fold(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
-                const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
-                float *__restrict__ power, int split) {
-  constexpr int kNF = kN * D;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CtaSmemF<D, STAGE> &sm = *reinterpret_cast<CtaSmemF<D, STAGE> *>(smem_raw);
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
-    const int p = i >> 5, l = i & 31;
-    float s0, c0, s1, c1;
-    sincospif(2.0f * (float)(p * l) / (float)kN, &s0, &c0);
-    sincospif(2.0f * (float)((p + 16) * l) / (float)kN, &s1, &c1);
-    sm.tw_a[p][l] = make_float4(c0, c1, s0, s1);
-    sincospif(2.0f * (float)(2 * p * l) / (float)kN, &s0, &c0);
-    sincospif(2.0f * (float)((2 * p + 1) * l) / (float)kN, &s1, &c1);
-    sm.tw_b[p][l] = make_float4(c0, c1, s0, s1);
-#pragma unroll
-    for (int q = 1; q < D; ++q) {
-      sincospif(2.0f * (float)(q * (l + 64 * p)) / (float)kNF, &s0, &c0);
-      sincospif(2.0f * (float)(q * (l + 64 * p + 32)) / (float)kNF, &s1, &c1);
-      sm.tw_c[q - 1][p][l] = make_float4(c0, c1, s0, s1);
-    }
-  }
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    sm.row[i] = rows[i];
-    if (COI) sm.coi[i] = coi[i];
-  }
-  __syncthreads();
-  WarpSmemF<STAGE> &ws = sm.w[warp];
-  float *const yr = ws.trr, *const yi = ws.tri;      // single-pass rows never touch the transpose buffer
-  // consecutive series go to different SMs: a small batch spreads over the machine
-  const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
-  const int64_t nwarps = (int64_t)gridDim.x * kWarpsDefault;
-  const float lanef = (float)lane;
-  const int tidx = 2 * (lane & 15) + (lane >> 4);
-  float2 R[16], I[16];
-
-  // one warp item = one series and every split-th scale row from row c on (see k_cwt_fast_1024)
-  for (int64_t it = gwarp; it < batch * split; it += nwarps) {
-    const int64_t b = it / split;
-    const int c = (int)(it - b * split);
-    const float2 *xh = xhat + b * kNF + lane;
-#pragma unroll 1
-    for (int sq = D * c; sq < D * S; sq = (sq % D == D - 1) ? sq + D * (split - 1) + 1 : sq + 1) {
-      const int s = sq / D, q = sq % D;
-      const RowParam rp = sm.row[s];
-      const int L = rp.L, two_pass = rp.multi;
-      const float zl = fmaf(rp.a, lanef, -f0);       // s*w_k - f0 at k = lane
-      if (two_pass) {
-        const int M = 1 << (rp.L - 1);
-        const float2 zl2 = make_float2(zl, fmaf(rp.a, 32.0f, zl));
-        const float2 a64 = bc(rp.a * 64.0f);
-        const float2 ln2 = bc(rp.lognorm);
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          if (M > below_pow2_16(m)) {
-            const float2 z = fma2(a64, bc((float)m), zl2);
-            const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);
-            const float2 d = make_float2(ex2(e.x), ex2(e.y));
-            const float2 v0 = ldg_keep(xh + 64 * m), v1 = ldg_keep(xh + 64 * m + 32);
-            float2 vr = mul2(make_float2(v0.x, v1.x), d), vi = mul2(make_float2(v0.y, v1.y), d);
-            if (q) {
-              const float4 t = sm.tw_c[q - 1][m][lane];
-              const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
-              const float2 ur = fma2(vi, neg2(twi), mul2(vr, twr));
-              vi = fma2(vr, twi, mul2(vi, twr));
-              vr = ur;
-            }
-            R[br4(m)] = vr;
-            I[br4(m)] = vi;
-          }
-        }
-      } else {
-        const float d = ex2(fmaf(zl * zl, -0.72134752044f, rp.lognorm));
-        const float2 v0 = ldg_keep(xh);
-        float ar = v0.x * d, ai = v0.y * d;
-        if (q) {
-          const float4 t = sm.tw_c[q - 1][0][lane];  // (cos, ., sin, .) of 2*pi*q*lane/N
-          const float ur = fmaf(-ai, t.z, ar * t.x);
-          ai = fmaf(ar, t.z, ai * t.x);
-          ar = ur;
-        }
-        yr[lane] = ar;
-        yi[lane] = ai;
-        __syncwarp();
-        const int M = 1 << (rp.L - 1);
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          if (M > below_pow2_16(m)) {
-            const float2 y_r = *reinterpret_cast<const float2 *>(&yr[2 * m]);
-            const float2 y_i = *reinterpret_cast<const float2 *>(&yi[2 * m]);
-            const float4 t = sm.tw_b[m][lane];
-            const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
-            R[br4(m)] = fma2(y_i, neg2(twi), mul2(y_r, twr));
-            I[br4(m)] = fma2(y_r, twi, mul2(y_i, twr));
-          }
-        }
-        __syncwarp();
-      }
-      fft32::dit32(R, I, L);
-      if (two_pass) {
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const float4 t = sm.tw_a[p][lane];
-          const float2 twr = make_float2(t.x, t.y), twi = make_float2(t.z, t.w);
-          const float2 vr = fma2(I[p], neg2(twi), mul2(R[p], twr));
-          const float2 vi = fma2(R[p], twi, mul2(I[p], twr));
-          *reinterpret_cast<float2 *>(&ws.trr[lane * kTrStride + 2 * p]) = vr;
-          *reinterpret_cast<float2 *>(&ws.tri[lane * kTrStride + 2 * p]) = vi;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          R[br4(m)] = make_float2(ws.trr[(2 * m) * kTrStride + tidx], ws.trr[(2 * m + 1) * kTrStride + tidx]);
-          I[br4(m)] = make_float2(ws.tri[(2 * m) * kTrStride + tidx], ws.tri[(2 * m + 1) * kTrStride + tidx]);
-        }
-        __syncwarp();
-        fft32::dit32(R, I, 5);
-      }
-      // position p holds u = lane + 32 p (.x) and u + 512 (.y); this phase is sample t = 2 u + q.
-      // Phase 0 waits in shared memory (same lane writes and reads it: no synchronisation); phase 1
-      // pairs it with its own values, so a lane stores (t, t + 1) as one 8-byte word and a warp
-      // store covers 256 contiguous bytes -- whole 128-byte lines instead of every other float
-      // (stride-2 stores cost two L2 write requests per sector and partial-sector DRAM writes).
-      static_assert(D == 2, "the staged store pairs two phases");
-      const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
-      const int u2 = 2 * lane;                        // t of phase 0 at p = 0
-      if (!STAGE) {
-        // each phase stores its own samples at stride 2; the halves of a line meet in L2
-        float *orow = power + (b * S + s) * (int64_t)n0 + u2 + q;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-          const int ta = u2 + q + 64 * p, tb = ta + 1024;
-          if (COI) {
-            if (ta < tlo || ta > thi) pw.x = NAN;
-            if (tb < tlo || tb > thi) pw.y = NAN;
-          }
-          if (ta < n0) st_stream(orow + 64 * p, pw.x);
-          if (tb < n0) st_stream(orow + 64 * p + 1024, pw.y);
-        }
-      } else if (q == 0) {
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-          if (COI) {
-            const int ta = u2 + 64 * p, tb = ta + 1024;
-            if (ta < tlo || ta > thi) pw.x = NAN;
-            if (tb < tlo || tb > thi) pw.y = NAN;
-          }
-          ws.stage[p][lane] = pw;
-        }
-      } else {
-        float *orow = power + (b * S + s) * (int64_t)n0 + u2;
-        const bool al8 = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);   // odd n0: every other row is only 4-byte aligned
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          float2 pw = fma2(R[p], R[p], mul2(I[p], I[p]));
-          const float2 p0 = ws.stage[p][lane];
-          const int ta = u2 + 64 * p, tb = ta + 1024;    // phase-0 samples; phase 1 is ta + 1, tb + 1
-          if (COI) {
-            if (ta + 1 < tlo || ta + 1 > thi) pw.x = NAN;
-            if (tb + 1 < tlo || tb + 1 > thi) pw.y = NAN;
-          }
-          if (al8 && ta + 1 < n0) st_stream2(orow + 64 * p, make_float2(p0.x, pw.x));
-          else {
-            if (ta < n0) st_stream(orow + 64 * p, p0.x);
-            if (ta + 1 < n0) st_stream(orow + 64 * p + 1, pw.x);
-          }
-          if (al8 && tb + 1 < n0) st_stream2(orow + 64 * p + 1024, make_float2(p0.y, pw.y));
-          else {
-            if (tb < n0) st_stream(orow + 64 * p + 1024, p0.y);
-            if (tb + 1 < n0) st_stream(orow + 64 * p + 1025, pw.y);
-          }
-        }
-      }
-    }
-  }
-}
-
-
-// ---- nfft = 2048, two warps per scale row (k_cwt_pair_2048) ---------------------------------------
-// Decimation in frequency instead of in time: with E[u], G[u] the 1024-point inverse transforms of the
-// even and of the odd bins of the one-sided spectrum Y[k], k < 1024,
+// Two warps per scale row (k_cwt_pair_2048).  Decimation in frequency: with E[u], G[u] the 1024-point
+// inverse transforms of the even and of the odd bins of the one-sided spectrum Y[k], k < 1024,
 //   x[u]        = E[u] + w2048^u G[u]
 //   x[u + 1024] = E[u] - w2048^u G[u],          u < 1024.
-// Warp h of a pair owns the bins of parity h (512 of them: step A of its 1024-point transform has at
-// most 16 non-zero inputs, one butterfly stage less than the time-decimated passes above, and a row
-// is single-pass up to k_hi < 64 instead of 32), the odd warp multiplies by w2048^u, and the two
-// exchange half of their outputs through a 4 KB mailbox: warp 0 finishes u < 512, warp 1 u >= 512,
-// each storing whole 128-byte lines of x[u] and x[u + 1024] -- no strided stores, no staging, and no
-// transform of samples past n0 is combined or stored.
-// The seven pairs of a CTA work on ONE series: its spectrum X^ (8 KB) arrives by a TMA bulk copy into a
-// ring of three slots (mbarrier full / done), so no row ever re-reads global memory, and the pairs
-// draw rows from a shared counter (small scales first, they are the expensive ones).
+// Warp h of a pair owns the bins of parity h: 512 of them, so step A of its 1024-point transform has at
+// most 16 non-zero inputs (one butterfly stage less than a full pass) and a row is single-pass up to
+// k_hi < 64 instead of 32.  The odd warp multiplies by w2048^u, then the two swap half of their packed
+// registers through mailboxes that alias the (by then idle) transpose buffers: warp 0 finishes register
+// positions p < 8, warp 1 p >= 8, each storing whole 128-byte lines of x[u], x[u + 512], x[u + 1024] and
+// x[u + 1536] -- no strided stores, no staging, and nothing past n0 is combined or stored.
+// The eight pairs of a CTA work on ONE series: its spectrum X^ (8 KB, in the layout the warps load with one
+// 16-byte access per packed pair) arrives by a TMA bulk copy into a ring of three slots (mbarrier full /
+// done), so no row ever re-reads global memory, and the pairs draw rows from a shared counter (small scales
+// first, they are the expensive ones).
+// History: rounds 1-2 ran this shape as two time-decimated 1024-point passes per row in one warp (samples
+// 2u + q, `k_cwt_fast_fold`: stride-2 or staged stores, X^ re-read through L1; 4.0e11 coeff/s at 1346
+// samples, 5.6e11 at 2048 -- DESIGN.md section 4 keeps its measurements); this kernel is faster at every batch
+// size (4.5e11 / 6.6e11, 0.040 ms against 0.055 ms for 12 series) and replaced it.
+constexpr int kMaxRowsF = 128;
+constexpr int kMinBatchF = 12;
 constexpr int kPairWarps = 16;
 constexpr int kPairs = kPairWarps / 2;
 constexpr int kRing = 3;
@@ -1001,25 +766,21 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 }
 
 
-// FP32 CWT + power rows for nfft = 2048 from forward spectra xhat [batch, nfft] (cwt.cu tries
-// this after its forward-FFT kernel).  Returns 1 when the shape is not covered.
-// true: cwt_fast_fold_try runs the two-warps-per-row kernel for this shape and wants the forward
-// spectra in its layout (CtaSmemP::xh; written by k_fwd_fft_pair2048 in cwt.cu)
+// true: cwt_pair2048_try runs this shape and wants the forward spectra in its layout (CtaSmemP::xh; written by
+// k_fwd_fft_pair2048 in cwt.cu).  The kernel stores the first 1024 samples of a row unconditionally (n0 > 1024).
+// The rows of a series are split over CTAs when the batch is small, but this path also pays for the separate
+// forward-FFT launch: 0.040 ms for 12 series against 0.021 ms + 1.7 us per series for the generic kernel.
 bool cwt_pair2048_covers(int64_t batch, int n0, int nfft, int S, double f0) {
-  static const bool use_fold_env = std::getenv("WTB_CWT_FOLD") != nullptr;   // the time-decimated kernel, kept for A/B runs
-  return nfft == 2 * kN && f0 >= kZCut && S <= kMaxRowsF && batch >= min_fast_batch(kMinBatchF) && n0 > kN && !use_fold_env;
+  return nfft == 2 * kN && f0 >= kZCut && S <= kMaxRowsF && batch >= min_fast_batch(kMinBatchF) && n0 > kN;
 }
 
-int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
-                      int flags, float *d_power, cudaStream_t st) {
+// FP32 CWT + power rows for nfft = 2048 from forward spectra in pair layout (cwt.cu tries this after its
+// forward-FFT kernel).  Returns 1 when the shape is not covered.
+int cwt_pair2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
+                     int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
-  // The rows of a series are split over warps when the batch is small, but this path also pays
-  // for the separate forward-FFT launch: 0.038 ms flat up to 32 series against 0.021 ms + 1.7 us
-  // per series for the generic kernel -- measured crossover at about 12 series.
-  if (nfft != 2 * kN || f0 < kZCut || S > kMaxRowsF || batch < min_fast_batch(kMinBatchF)) return 1;
+  if (!cwt_pair2048_covers(batch, n0, nfft, S, f0)) return 1;
   const bool coi = flags & WTB_COI_MASK;
-  // the pair kernel stores the first 1024 samples of a row unconditionally (n0 > 1024)
-  const bool use_fold = !cwt_pair2048_covers(batch, n0, nfft, S, f0);
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
     const double a = ax.scales[s] / dt * 2.0 * kPi / nfft;
@@ -1028,15 +789,10 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
     RowParam &r = rows[s];
     r.a = (float)a;
     r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / nfft);
-    if (use_fold) {
-      r.multi = khi >= 32;
-      r.L = r.multi ? std::max(1, std::min(5, ilog2(khi / 32 + 1))) : ilog2(khi + 1);
-    } else {
-      // pair kernel: a warp transforms the bins of one parity, j = k / 2 <= jhi < 512
-      const int jhi = khi / 2;
-      r.multi = jhi >= 32;
-      r.L = r.multi ? std::max(1, std::min(4, ilog2(jhi / 32 + 1))) : std::max(1, ilog2(jhi + 1));
-    }
+    // a warp transforms the bins of one parity, j = k / 2 <= jhi < 512
+    const int jhi = khi / 2;
+    r.multi = jhi >= 32;
+    r.L = r.multi ? std::max(1, std::min(4, ilog2(jhi / 32 + 1))) : std::max(1, ilog2(jhi + 1));
   }
   // the caller's arena holds xhat: row parameters go to the per-thread parameter buffer
   void *prm = nullptr;
@@ -1051,36 +807,17 @@ int cwt_fast_fold_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, dou
     d_coi = (ushort2 *)(d_rows + kMaxRowsF);
     WTB_CUDA(cudaMemcpyAsync(d_coi, rng.data(), sizeof(ushort2) * S, cudaMemcpyHostToDevice, st));
   }
-  if (!use_fold) {
-    // fewer series than SMs: the rows of a series are dealt to up to 16 CTAs
-    const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), (int64_t)sm_count() / batch));
-    const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
-    WTB_REQUIRE(batch * split < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
-    auto run = [&](auto kern) -> int {
-      WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmemP)));
-      kern<<<grid, kPairWarps * 32, sizeof(CtaSmemP), st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
-      WTB_LAUNCH_CHECK();
-      return WTB_OK;
-    };
-    return coi ? run(k_cwt_pair_2048<true>) : run(k_cwt_pair_2048<false>);
-  }
-  const int64_t machine_warps = (int64_t)sm_count() * kWarpsDefault;
-  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), machine_warps / batch));
+  // fewer series than SMs: the rows of a series are dealt to up to 16 CTAs
+  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), (int64_t)sm_count() / batch));
   const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
-  static_assert(sizeof(CtaSmemF<2, true>) <= 227 * 1024, "the fold kernel's tables, transpose buffers and staging rows must fit one CTA");
-  int stage_min = kStageMinN0;
-  if (const char *e = std::getenv("WTB_FOLD_STAGE_MIN")) stage_min = std::atoi(e);
-  const bool stage = n0 > stage_min;
-  auto run = [&](auto kern, size_t smem) -> int {
-    WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kWarpsDefault * 32, smem, st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
+  WTB_REQUIRE(batch * split < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
+  auto run = [&](auto kern) -> int {
+    WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmemP)));
+    kern<<<grid, kPairWarps * 32, sizeof(CtaSmemP), st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   };
-  if (stage) return coi ? run(k_cwt_fast_fold<2, true, true>, sizeof(CtaSmemF<2, true>))
-                        : run(k_cwt_fast_fold<2, false, true>, sizeof(CtaSmemF<2, true>));
-  return coi ? run(k_cwt_fast_fold<2, true, false>, sizeof(CtaSmemF<2, false>))
-             : run(k_cwt_fast_fold<2, false, false>, sizeof(CtaSmemF<2, false>));
+  return coi ? run(k_cwt_pair_2048<true>) : run(k_cwt_pair_2048<false>);
 }
 
 }  // namespace wtb

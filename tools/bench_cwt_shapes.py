@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Device-resident throughput of the fused CWT+power paths by series shape, against the HBM roofline.
+"""Device-resident throughput of the fused CWT+power paths by series shape, against the roofline north_star
+names: the slower of FFT flops at the nominal FP32 peak and coefficient bytes at the measured HBM bandwidth.
 
     python tools/bench_cwt_shapes.py
 
-Unit = one series; algorithmic bytes 4*n0*(1 + S) (FP32 series in, power plane out).  Shapes: BASELINE
+Unit = one series; algorithmic bytes 4*n0*(1 + S) (FP32 series in, power plane out), algorithmic flop
+5 N log2 N + S (5 N log2 N + 5 N) with N the FFT length.  Shapes: BASELINE
 cfg1 (1346 samples -> nfft 2048, 85 scales), full 2048, cfg4 (1024 x 120) and the nfft-4096 rows;
 each also through the generic Stockham kernel for reference.
 """
@@ -16,6 +18,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
+FP32_PEAK_TF = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal non-tensor FP32
 sys.path.insert(0, str(ROOT))
 
 
@@ -59,8 +62,16 @@ def main():
             torch.cuda.synchronize()
             t = e0.elapsed_time(e1) * 1e-3 / 5
             gbs = 4.0 * n0 * (1 + S) * nb / t / 1e9
-            print(json.dumps({"shape": label, "n0": n0, "scales": S, "batch": nb, "kernel": "generic" if generic else "fast",
-                              "ms": t * 1e3, "coeff_per_s": nb * S * n0 / t, "achieved_GBs": gbs, "frac_hbm": gbs / peak}))
+            nfft = 1 << (n0 - 1).bit_length()
+            lg = nfft.bit_length() - 1
+            flop = 5.0 * nfft * lg + S * (5.0 * nfft * lg + 5.0 * nfft)
+            tfs = flop * nb / t / 1e12
+            t_hbm, t_fp32 = 4.0 * n0 * (1 + S) / (peak * 1e9), flop / (FP32_PEAK_TF * 1e12)
+            print(json.dumps({"shape": label, "n0": n0, "nfft": nfft, "scales": S, "batch": nb,
+                              "kernel": "generic" if generic else "fast", "ms": t * 1e3, "coeff_per_s": nb * S * n0 / t,
+                              "achieved_GBs": gbs, "frac_hbm": gbs / peak, "achieved_TFLOPs": tfs,
+                              "frac_fp32_nominal": tfs / FP32_PEAK_TF, "bound": "fp32" if t_fp32 > t_hbm else "hbm",
+                              "frac_roofline": max(t_hbm, t_fp32) * nb / t}))
         del x, out
 
 

@@ -353,10 +353,11 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 //   x[u + 1024] = E[u] - w2048^u G[u],          u < 1024.
 // Warp h of a pair owns the bins of parity h: 512 of them, so step A of its 1024-point transform has at
 // most 16 non-zero inputs (one butterfly stage less than a full pass) and a row is single-pass up to
-// k_hi < 64 instead of 32.  The odd warp multiplies by w2048^u, then the two swap half of their packed
-// registers through mailboxes that alias the (by then idle) transpose buffers: warp 0 finishes register
-// positions p < 8, warp 1 p >= 8, each storing whole 128-byte lines of x[u], x[u + 512], x[u + 1024] and
-// x[u + 1536] -- no strided stores, no staging, and nothing past n0 is combined or stored.
+// k_hi < 64 instead of 32.  The two warps swap half of their packed registers through mailboxes that alias
+// the (by then idle) transpose buffers: warp 0 finishes register positions p < 8, warp 1 p >= 8; the twiddle
+// w2048^u rides in the additions of the finishing warp (x[u] = e + w g as two FFMA2 per component,
+// x[u + 1024] = 2 e - x[u]), so both warps do the same work, and each stores whole 128-byte lines of x[u],
+// x[u + 512], x[u + 1024] and x[u + 1536] -- no strided stores, no staging, nothing past n0 is combined or stored.
 // The eight pairs of a CTA work on ONE series: its spectrum X^ (8 KB, in the layout the warps load with one
 // 16-byte access per packed pair) arrives by a TMA bulk copy into a ring of three slots (mbarrier full /
 // done), so no row ever re-reads global memory, and the pairs draw rows from a shared counter (small scales
@@ -364,7 +365,7 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 // History: rounds 1-2 ran this shape as two time-decimated 1024-point passes per row in one warp (samples
 // 2u + q, `k_cwt_fast_fold`: stride-2 or staged stores, X^ re-read through L1; 4.0e11 coeff/s at 1346
 // samples, 5.6e11 at 2048 -- DESIGN.md section 4 keeps its measurements); this kernel is faster at every batch
-// size (4.5e11 / 6.6e11, 0.040 ms against 0.055 ms for 12 series) and replaced it.
+// size (4.6e11 / 6.9e11, 0.040 ms against 0.055 ms for 12 series) and replaced it.
 constexpr int kMaxRowsF = 128;
 constexpr int kMinBatchF = 12;
 constexpr int kPairWarps = 16;
@@ -577,19 +578,8 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         __syncwarp();
         fft32::dit32(R, I, 5);
       }
-      // position p holds u = lane + 32 p (.x) and u + 512 (.y) of this warp's 1024-point transform
-      if (h) {
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const float4 t = sm.tw_o[p][lane];
-          const float2 ta = make_float2(t.x, t.y), tb = make_float2(t.z, t.w);
-          const float2 vr = fma2(I[p], neg2(tb), mul2(R[p], ta));
-          I[p] = fma2(R[p], tb, mul2(I[p], ta));
-          R[p] = vr;
-        }
-      }
-      // The mailboxes live in the transpose buffers: both warps must be past their step-B loads
-      __syncwarp();
+      // position p holds u = lane + 32 p (.x) and u + 512 (.y) of this warp's 1024-point transform.
+      // The mailboxes live in the transpose buffers: both warps must be past their step-B loads.
       pair_sync(pair);
       if (h) {
 #pragma unroll
@@ -613,10 +603,13 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
       const int t0 = lane + 256 * h;
       float *orow = power + ((int64_t)b * S + s) * (int64_t)n0 + t0;
-      // e = even-bin transform, o = twiddled odd-bin transform, both at u = t0 + 32 p (.x) and u + 512 (.y):
-      // x[u] = e + o, x[u + 1024] = e - o -> four whole lines per position
-      auto finish = [&](const int p, const float2 er, const float2 ei, const float2 orr, const float2 oi) {
-        const float2 lr = add2(er, orr), li = add2(ei, oi);
+      // e = even-bin transform, g = odd-bin transform, both at u = t0 + 32 p (.x) and u + 512 (.y), w = w2048^u as
+      // (c, -s | s, c) for the two halves (w2048^(u+512) = i w2048^u):  x[u] = e + w g,  x[u + 1024] = e - w g = 2 e - x[u].
+      // The twiddle rides in the additions (the receiving side applies it: both warps do the same work), and each
+      // position leaves as four whole lines.
+      auto finish = [&](const int p, const float2 er, const float2 ei, const float2 gr, const float2 gi, const float4 w) {
+        const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
+        const float2 lr = fma2(gr, wa, fma2(gi, neg2(wb), er)), li = fma2(gi, wa, fma2(gr, wb, ei));
         float2 lo = fma2(lr, lr, mul2(li, li));      // |x[u]|^2, |x[u + 512]|^2
         const int ta = t0 + 32 * p;
         if (COI) {
@@ -626,7 +619,7 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         __stcs(orow + 32 * p, lo.x);                 // n0 > 1024: the first half is always inside the row
         __stcs(orow + 32 * p + 512, lo.y);
         if (kN + 256 * h + 32 * p < n0) {            // warp-uniform: some lane still has a sample in the second half
-          const float2 hr = fma2(orr, bc(-1.0f), er), hi = fma2(oi, bc(-1.0f), ei);
+          const float2 hr = fma2(er, bc(2.0f), neg2(lr)), hi = fma2(ei, bc(2.0f), neg2(li));
           float2 hp = fma2(hr, hr, mul2(hi, hi));    // |x[u + 1024]|^2, |x[u + 1536]|^2
           if (COI) {
             if (ta + 1024 < tlo || ta + 1024 > thi) hp.x = NAN;
@@ -638,10 +631,11 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       };
       if (h) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) finish(p, my_mr[p * 32 + lane], my_mi[p * 32 + lane], R[p + 8], I[p + 8]);
+        for (int p = 0; p < 8; ++p)
+          finish(p, my_mr[p * 32 + lane], my_mi[p * 32 + lane], R[p + 8], I[p + 8], sm.tw_o[p + 8][lane]);
       } else {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) finish(p, R[p], I[p], my_mr[p * 32 + lane], my_mi[p * 32 + lane]);
+        for (int p = 0; p < 8; ++p) finish(p, R[p], I[p], my_mr[p * 32 + lane], my_mi[p * 32 + lane], sm.tw_o[p][lane]);
       }
     }
     if (leader) mbar_arrive(&sm.done[slot]);

@@ -103,10 +103,11 @@ def test_cwt_coi_mask(shim):
     assert np.array_equal(p_mask[~outside], p[~outside])
 
 
-@pytest.mark.parametrize("n0,batch", [(400, 5), (512, 4), (700, 3), (1024, 3), (1346, 13), (2048, 12), (3351, 3), (4096, 2)])
+@pytest.mark.parametrize("n0,batch", [(400, 5), (512, 4), (700, 3), (1024, 3), (1346, 13), (2048, 12), (3351, 3), (4096, 2),
+                                      (3351, 13), (4096, 12)])
 def test_cwt_coi_mask_fused_fast_kernels(shim, n0, batch):
     """north_star (1): the cone-of-influence mask is fused into the FP32 fast kernels' store loops
-    (nfft 512 two-series, 1024, 2048 warp pairs, 4096 rows).  Inside the cone the power is bit-equal to
+    (nfft 512 two-series, 1024, 2048 warp pairs, 4096 register rows and warp quads).  Inside the cone the power is bit-equal to
     the unmasked fast kernel, outside it is NaN, and the mask itself equals the oracle's
     `period > coi` (the generic kernel's, too)."""
     x = np.random.default_rng(n0).standard_normal((batch, n0))
@@ -276,6 +277,37 @@ def test_cwt_fp32_nfft2048_interleaved_passes(shim, monkeypatch, n0, dj, J):
     small, _ = shim.cwt_morlet(x[:5], DT, dj, 2 * DT, J, f64=False)
     assert np.array_equal(small, gen[:5])
 
+
+
+@pytest.mark.parametrize("n0,dj,J,batch", [(3351, 1 / 8, 65, 300), (4096, 1 / 12, 100, 150), (2049, 1 / 4, -1, 12),
+                                            (3000, 1 / 6, 40, 450)])
+def test_cwt_fp32_nfft4096_warp_quads(shim, monkeypatch, n0, dj, J, batch):
+    """Batches (>= 12) of 2049..4096-sample series take the four-warps-per-row kernel (bins k = 4 j + r per
+    warp, radix-4 combine through the transpose buffers).  Oracle parity on sampled series, generic-kernel
+    parity on all; 300 and 450 series give every CTA two to four series (its two-slot spectrum ring is
+    refilled), 12 series split their rows over CTAs."""
+    rng = np.random.default_rng(n0)
+    x = rng.standard_normal((batch, n0)).cumsum(axis=1) * 0.05 + rng.standard_normal((batch, n0))
+    power, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False)
+    gen, _ = shim.cwt_morlet(x, DT, dj, 2 * DT, J, f64=False, generic_only=True)
+    assert power.shape == gen.shape and power.shape[0] == batch and power.shape[2] == n0
+    for b in range(batch):
+        ok, err = normwise_close(power[b], gen[b], 1e-4)
+        assert ok, f"series {b}: {err:.3e} vs the generic kernel"
+    for b in (0, batch // 2, batch - 1):
+        ref = np.abs(_oracle_plane(x[b], DT, dj, 2 * DT, J)) ** 2
+        ok, err = normwise_close(power[b], ref, 1e-4)
+        assert ok, f"series {b}: {err:.3e} vs the oracle"
+    # a series' numbers do not depend on the batch it came in (split over CTAs or not)
+    first, _ = shim.cwt_morlet(x[:13], DT, dj, 2 * DT, J, f64=False)
+    assert np.array_equal(first, power[:13])
+    # below the default threshold (12 series) the register-row kernel (k_cwt_rows_4096) serves the call
+    monkeypatch.delenv("WTB_CWT_MIN_BATCH")
+    small, _ = shim.cwt_morlet(x[:5], DT, dj, 2 * DT, J, f64=False)
+    assert not np.array_equal(small, power[:5])
+    for b in range(5):
+        ok, err = normwise_close(small[b], gen[b], 1e-4)
+        assert ok, f"series {b}: {err:.3e} (register rows) vs the generic kernel"
 
 
 def test_cwt_fp32_dispatch_fuzz(shim):

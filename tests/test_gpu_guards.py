@@ -28,7 +28,7 @@ def _intact(torch, buf, n, pattern):
 
 @pytest.mark.parametrize("n0,batch,J,dj", [(1024, 37, 119, 1 / 12), (777, 5, 100, 1 / 12), (400, 7, 91, 1 / 12),
                                            (511, 1, 60, 1 / 8), (1346, 13, 84, 1 / 12), (2047, 14, 84, 1 / 12),
-                                           (1025, 12, 84, 1 / 12), (1537, 301, 40, 1 / 6),
+                                           (1025, 12, 84, 1 / 12), (1537, 301, 40, 1 / 6), (3351, 13, 65, 1 / 8), (2049, 150, 30, 1 / 4),
                                            (3351, 3, 65, 1 / 8), (4096, 2, 65, 1 / 8), (100, 3, 20, 1 / 4)])
 def test_cwt_kernels_stay_inside_their_output(shim, n0, batch, J, dj):
     import torch

@@ -11,12 +11,12 @@ namespace wtb {
 int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
                  double f0, int flags, float *d_power, cudaStream_t st);
 
-// implemented in cwt_fast.cu (two warps per row for nfft = 2048, spectra in pair layout); 1 = not covered
-int cwt_pair2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
-                      int flags, float *d_power, cudaStream_t st);
+// implemented in cwt_fast.cu (two / four warps per row for nfft = 2048 / 4096, spectra in group layout); 1 = not covered
+int cwt_dif_try(const float2 *d_layout, int64_t stride, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
+                double f0, int flags, float *d_power, cudaStream_t st);
 
-// implemented in cwt_fast.cu: the shape runs the two-warps-per-row kernel, which reads the spectra in pair layout
-bool cwt_pair2048_covers(int64_t batch, int n0, int nfft, int S, double f0);
+// implemented in cwt_fast.cu: the shape runs those kernels, which read the spectra in group layout
+bool cwt_dif_covers(int64_t batch, int n0, int nfft, int S, double f0);
 
 // implemented in wct_fast.cu (register-FFT rows for nfft = 4096); returns 1 when not covered
 int cwt_rows_4096_try(const float2 *d_xhat, int64_t batch, int n0, int N, double dt, const Axes &ax, double f0,
@@ -43,6 +43,18 @@ __global__ void k_fwd_fft_pair2048(const float *__restrict__ x, int n0, FftPlan<
   for (int i = threadIdx.x; i < 2 * 8 * 32; i += blockDim.x) {
     const int lane = i & 31, m = (i >> 5) & 7, h = i >> 8;
     const float2 v0 = r[2 * (lane + 64 * m) + h], v1 = r[2 * (lane + 64 * m) + h + 64];
+    o[i] = make_float4(v0.x, v1.x, v0.y, v1.y);
+  }
+}
+
+// The same layout for N = 4096 (four warps per row: k0 = 4 (lane + 64 m) + r, k1 = k0 + 128, r < 4; 16 KB), built from
+// the natural-order spectrum of the radix-16 forward kernel into the unused negative-frequency half of the row.
+__global__ void k_dif_layout4096(float2 *__restrict__ xhat) {
+  const float2 *r = xhat + (int64_t)blockIdx.x * 4096;
+  float4 *o = reinterpret_cast<float4 *>(xhat + (int64_t)blockIdx.x * 4096 + 2048);
+  for (int i = threadIdx.x; i < 4 * 8 * 32; i += blockDim.x) {
+    const int lane = i & 31, m = (i >> 5) & 7, h = i >> 8;
+    const float2 v0 = r[4 * (lane + 64 * m) + h], v1 = r[4 * (lane + 64 * m) + h + 128];
     o[i] = make_float4(v0.x, v1.x, v0.y, v1.y);
   }
 }
@@ -144,23 +156,28 @@ static int cwt_device(const T *d_x, int64_t batch, int n0, int N, double dt, con
       fwd_rc = fwd_fft_4096_try((const float *)d_x, batch, n0, N, (float2 *)d_xhat, st);
     if (fwd_rc < 0) return fwd_rc;
   }
-  bool pair_layout = false;
+  bool dif = false;            // the two / four-warps-per-row kernels take this shape (spectra in group layout)
   if constexpr (sizeof(T) == 4) {
-    pair_layout = fwd_rc == 1 && mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef &&
-                  cwt_pair2048_covers(batch, n0, N, S, f0);
-    if (pair_layout) {
+    dif = mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY) && d_power && !d_coef && cwt_dif_covers(batch, n0, N, S, f0);
+    if (dif && N == 2048) {
       WTB_CUDA(cudaFuncSetAttribute(k_fwd_fft_pair2048, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_fwd_fft_pair2048<<<(unsigned)batch, threads, smem, st>>>((const float *)d_x, n0, plan, (float2 *)d_xhat);
       WTB_LAUNCH_CHECK();
+      fwd_rc = 0;
     }
   }
-  if (fwd_rc == 1 && !pair_layout) {
+  if (fwd_rc == 1) {
     k_fwd_fft<T><<<(unsigned)batch, threads, smem, st>>>(d_x, n0, plan, d_xhat);
     WTB_LAUNCH_CHECK();
   }
   if constexpr (sizeof(T) == 4) {
-    if (pair_layout) {
-      const int rc = cwt_pair2048_try((const float2 *)d_xhat, batch, n0, N, dt, ax, f0, flags, (float *)d_power, st);
+    if (dif) {
+      if (N == 4096) {
+        k_dif_layout4096<<<(unsigned)batch, 256, 0, st>>>((float2 *)d_xhat);
+        WTB_LAUNCH_CHECK();
+      }
+      const int rc = cwt_dif_try((const float2 *)d_xhat + (N == 4096 ? 2048 : 0), N, batch, n0, N, dt, ax, f0, flags,
+                                 (float *)d_power, st);
       if (rc != 1) return rc;
     }
     if (mo.kind == WTB_MORLET && !(flags & WTB_GENERIC_ONLY)) {

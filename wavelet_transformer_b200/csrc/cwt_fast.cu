@@ -347,7 +347,7 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 
 
 // ---- nfft = 2048 (series of 1025..2048 samples, e.g. the reference's 1346-month CPI series) ----
-// Two warps per scale row (k_cwt_pair_2048).  Decimation in frequency: with E[u], G[u] the 1024-point
+// Two warps per scale row (k_cwt_dif<2>).  Decimation in frequency: with E[u], G[u] the 1024-point
 // inverse transforms of the even and of the odd bins of the one-sided spectrum Y[k], k < 1024,
 //   x[u]        = E[u] + w2048^u G[u]
 //   x[u + 1024] = E[u] - w2048^u G[u],          u < 1024.
@@ -368,34 +368,41 @@ k_cwt_fast_1024(const float *__restrict__ x, int64_t batch, int n0, int S,
 // size (4.6e11 / 6.9e11, 0.040 ms against 0.055 ms for 12 series) and replaced it.
 constexpr int kMaxRowsF = 128;
 constexpr int kMinBatchF = 12;
-constexpr int kPairWarps = 16;
-constexpr int kPairs = kPairWarps / 2;
-constexpr int kRing = 3;
+// nfft = 4096 (series of 2049..4096 samples) is the same kernel with D = 4 warps per row: warp r owns the bins
+// k = 4 j + r of the one-sided spectrum (k < 2048, again 512 per warp), and
+//   x[u + 1024 q] = sum_r i^(q r) w4096^(r u) G_r[u],   q = 0..3,
+// is a radix-4 butterfly of the four twiddled 1024-point transforms: every warp deals its 16 register positions
+// to the four mailboxes of the group (its own included, so that the finishing code has compile-time register
+// indices), warp g finishes positions 4g .. 4g+3 and stores eight whole lines per position.
+constexpr int kDifWarps = 16;
 
 struct alignas(16) WarpSmemP {
   float trr[32 * kTrStride];        // transpose buffer; its first 32 floats double as Y[k] of a single-pass row,
-  float tri[32 * kTrStride];        // its first 2 KB as the mailbox the partner warp fills (8 positions x 32 lanes x 8 B)
+  float tri[32 * kTrStride];        // its first 2 KB (D = 2) / 4 KB (D = 4) as the mailbox the group's warps fill
 };
 
-struct CtaSmemP {
+template <int D> struct CtaSmemP {
+  static constexpr int kRing = D == 2 ? 3 : 2;
+  static constexpr int kGroups = kDifWarps / D;
   float4 tw_a[16][32];              // as in CtaSmem: twiddles of the 1024-point transform
   float4 tw_b[16][32];
-  float4 tw_o[16][32];              // (c, -s, s, c) of w2048^(lane + 32 p): the pair (u, u + 512) of the odd half
-  float4 xh[kRing][2][8][32];       // X^ of the series in flight in pair layout (k_fwd_fft_pair2048): [parity h][m][lane] =
-                                    // (Re X^[k0], Re X^[k1], Im X^[k0], Im X^[k1]), k0 = 2 (lane + 64 m) + h, k1 = k0 + 64
+  float4 tw_o[D - 1][16][32];       // w_N^(r u), u = lane + 32 p, r = 1 .. D-1: (Re at u, Re at u + 512, Im at u, Im at u + 512)
+  float4 xh[kRing][D][8][32];       // X^ of the series in flight in group layout (k_fwd_fft_pair2048 / k_dif_layout): [r][m][lane] =
+                                    // (Re X^[k0], Re X^[k1], Im X^[k0], Im X^[k1]), k0 = D (lane + 64 m) + r, k1 = k0 + 32 D
   RowParam row[kMaxRowsF];
   ushort2 coi[kMaxRowsF];
   uint64_t full[kRing];             // TMA completion of a slot
-  uint64_t done[kRing];             // every pair has finished the slot's series
+  uint64_t done[kRing];             // every group has finished the slot's series
   int next_row[kRing];
-  int pair_row[2][kPairs];          // row drawn by the pair's leader, by series parity (the partner may still be
+  int group_row[2][kGroups];        // row drawn by the group's leader, by series parity (the other warps may still be
                                     // reading the last draw of one series when the leader draws for the next)
-  WarpSmemP w[kPairWarps];
+  WarpSmemP w[kDifWarps];
 };
-static_assert(sizeof(CtaSmemP) <= 227 * 1024, "the pair kernel's tables, ring and per-warp buffers must fit one CTA");
+static_assert(sizeof(CtaSmemP<2>) <= 227 * 1024 && sizeof(CtaSmemP<4>) <= 227 * 1024,
+              "the tables, ring and per-warp buffers of the decimation-in-frequency kernels must fit one CTA");
 
-__device__ __forceinline__ void pair_sync(int pair) {
-  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+template <int D> __device__ __forceinline__ void group_sync(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(32 * D) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -414,17 +421,20 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t phase) {
   return ok != 0;
 }
 
-template <bool COI>
-__global__ void __launch_bounds__(kPairWarps * 32, 1)
-k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
-                const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
-                float *__restrict__ power, int split) {
-  constexpr int kNF = 2 * kN;
+template <int D, bool COI>
+__global__ void __launch_bounds__(kDifWarps * 32, 1)
+k_cwt_dif(const float2 *__restrict__ xhat, int64_t xhat_stride, int64_t batch, int n0, int S,
+          const RowParam *__restrict__ rows, const ushort2 *__restrict__ coi, float f0,
+          float *__restrict__ power, int split) {
+  using Smem = CtaSmemP<D>;
+  constexpr int kRing = Smem::kRing, kGroups = Smem::kGroups;
+  constexpr int kNF = D * kN;
+  constexpr uint32_t kSlotBytes = sizeof(float4) * D * 8 * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CtaSmemP &sm = *reinterpret_cast<CtaSmemP *>(smem_raw);
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int pair = warp >> 1, h = warp & 1;
+  const int group = warp / D, h = warp % D;
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
     const int p = i >> 5, l = i & 31;
     float s0, c0, s1, c1;
@@ -434,8 +444,12 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     sincospif(2.0f * (float)(2 * p * l) / (float)kN, &s0, &c0);
     sincospif(2.0f * (float)((2 * p + 1) * l) / (float)kN, &s1, &c1);
     sm.tw_b[p][l] = make_float4(c0, c1, s0, s1);
-    sincospif(2.0f * (float)(l + 32 * p) / (float)kNF, &s0, &c0);      // w2048^(u + 512) = i w2048^u
-    sm.tw_o[p][l] = make_float4(c0, -s0, s0, c0);
+#pragma unroll
+    for (int r = 1; r < D; ++r) {
+      sincospif(2.0f * (float)(r * (l + 32 * p)) / (float)kNF, &s0, &c0);
+      sincospif(2.0f * (float)(r * (l + 32 * p + 512)) / (float)kNF, &s1, &c1);
+      sm.tw_o[r - 1][p][l] = make_float4(c0, c1, s0, s1);
+    }
   }
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     sm.row[i] = rows[i];
@@ -447,19 +461,19 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     const unsigned it = blockIdx.x + (unsigned)j * gridDim.x;
     const int slot = j % kRing;
     sm.next_row[slot] = 0;
-    mbar_expect_tx(&sm.full[slot], (uint32_t)(sizeof(float2) * kN));
-    tma_load_1d(&sm.xh[slot][0][0][0], xhat + (int64_t)(it / (unsigned)split) * kNF, (uint32_t)(sizeof(float2) * kN), &sm.full[slot]);
+    mbar_expect_tx(&sm.full[slot], kSlotBytes);
+    tma_load_1d(&sm.xh[slot][0][0][0], xhat + (int64_t)(it / (unsigned)split) * xhat_stride, kSlotBytes, &sm.full[slot]);
   };
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&sm.full[i], 1);
-      mbar_init(&sm.done[i], kPairs);
+      mbar_init(&sm.done[i], kGroups);
     }
     mbar_init_fence();
     for (; next_load < kRing && blockIdx.x + (unsigned)next_load * gridDim.x < items; ++next_load) issue_load(next_load);
   }
   __syncthreads();
-  // refill every slot whose series all pairs have left (thread 0, between rows: never blocks)
+  // refill every slot whose series all groups have left (thread 0, between rows: never blocks)
   auto refill = [&](bool block) {
     while (blockIdx.x + (unsigned)next_load * gridDim.x < items) {
       const int slot = next_load % kRing;
@@ -474,8 +488,7 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
   WarpSmemP &ws = sm.w[warp];
   float *const yr = ws.trr, *const yi = ws.tri;
   float2 *const my_mr = reinterpret_cast<float2 *>(ws.trr), *const my_mi = reinterpret_cast<float2 *>(ws.tri);
-  float2 *const wp_mr = reinterpret_cast<float2 *>(sm.w[warp ^ 1].trr), *const wp_mi = reinterpret_cast<float2 *>(sm.w[warp ^ 1].tri);
-  const float kf = (float)(2 * lane + h);           // this lane's first bin
+  const float kf = (float)(D * lane + h);           // this lane's first bin
   const int tidx = 2 * (lane & 15) + (lane >> 4);
   const bool leader = (h == 0 && lane == 0);
   float2 R[16], I[16];
@@ -487,13 +500,13 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
     const unsigned b = it / (unsigned)split;
     const int c = (int)(it - b * (unsigned)split);
     const int nrows = (S - c + split - 1) / split;
-    if (threadIdx.x == 0 && next_load <= i) refill(true);     // only when the pairs ran a whole ring apart
+    if (threadIdx.x == 0 && next_load <= i) refill(true);     // only when the groups ran a whole ring apart
     mbar_wait(&sm.full[slot], (uint32_t)((i / kRing) & 1));
     const float4 *xs = &sm.xh[slot][h][0][lane];
-    volatile int *const my_row = &sm.pair_row[i & 1][pair];
+    volatile int *const my_row = &sm.group_row[i & 1][group];
     if (leader) *my_row = atomicAdd(&sm.next_row[slot], 1);
     __syncwarp();
-    pair_sync(pair);
+    group_sync<D>(group);
 #pragma unroll 1
     for (;;) {
       const int r = *my_row;
@@ -501,17 +514,17 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
       const int s = c + split * r;
       const RowParam rp = sm.row[s];
       const int L = rp.L, two_pass = rp.multi;
-      const float zl = fmaf(rp.a, kf, -f0);         // s*w_k - f0 at k = 2 lane + h
+      const float zl = fmaf(rp.a, kf, -f0);         // s*w_k - f0 at k = D lane + h
       if (two_pass) {
-        // Y[2 (lane + 32 k2) + h] = X^ * daughter for k2 < 2^L <= 16, two k2 per packed op
+        // Y[D (lane + 32 k2) + h] = X^ * daughter for k2 < 2^L <= 16, two k2 per packed op
         const int M = 1 << (rp.L - 1);
-        const float2 zl2 = make_float2(zl, fmaf(rp.a, 64.0f, zl));
-        const float2 a128 = bc(rp.a * 128.0f);
+        const float2 zl2 = make_float2(zl, fmaf(rp.a, 32.0f * D, zl));
+        const float2 a64 = bc(rp.a * (64.0f * D));
         const float2 ln2 = bc(rp.lognorm);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
           if (M > below_pow2(m)) {
-            const float2 z = fma2(a128, bc((float)m), zl2);
+            const float2 z = fma2(a64, bc((float)m), zl2);
             const float2 e = fma2(mul2(z, z), bc(-0.72134752044f), ln2);
             const float2 d = make_float2(ex2(e.x), ex2(e.y));
             const float4 v = xs[32 * m];
@@ -579,19 +592,37 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         fft32::dit32(R, I, 5);
       }
       // position p holds u = lane + 32 p (.x) and u + 512 (.y) of this warp's 1024-point transform.
-      // The mailboxes live in the transpose buffers: both warps must be past their step-B loads.
-      pair_sync(pair);
-      if (h) {
+      // The mailboxes live in the transpose buffers: every warp of the group must be past its step-B loads.
+      group_sync<D>(group);
+      const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
+      float *const orow0 = power + ((int64_t)b * S + s) * (int64_t)n0 + lane;
+      if constexpr (D == 2) {
+        float2 *const wp_mr = reinterpret_cast<float2 *>(sm.w[warp ^ 1].trr), *const wp_mi = reinterpret_cast<float2 *>(sm.w[warp ^ 1].tri);
+        if (h) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {               // warp 0 finishes positions p < 8
-          wp_mr[p * 32 + lane] = R[p];
-          wp_mi[p * 32 + lane] = I[p];
+          for (int p = 0; p < 8; ++p) {               // warp 0 finishes positions p < 8
+            wp_mr[p * 32 + lane] = R[p];
+            wp_mi[p * 32 + lane] = I[p];
+          }
+        } else {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {               // warp 1 finishes positions p >= 8
+            wp_mr[p * 32 + lane] = R[p + 8];
+            wp_mi[p * 32 + lane] = I[p + 8];
+          }
         }
       } else {
+        // warp g of the group finishes positions 4 g .. 4 g + 3: slot [source h][position] of its mailbox
+        WarpSmemP *const gw = &sm.w[warp - h];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {               // warp 1 finishes positions p >= 8
-          wp_mr[p * 32 + lane] = R[p + 8];
-          wp_mi[p * 32 + lane] = I[p + 8];
+        for (int g = 0; g < D; ++g) {
+          float2 *const mr = reinterpret_cast<float2 *>(gw[g].trr) + (h * 4) * 32 + lane;
+          float2 *const mi = reinterpret_cast<float2 *>(gw[g].tri) + (h * 4) * 32 + lane;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mr[q * 32] = R[4 * g + q];
+            mi[q * 32] = I[4 * g + q];
+          }
         }
       }
       if (leader) {
@@ -599,43 +630,89 @@ k_cwt_pair_2048(const float2 *__restrict__ xhat, int64_t batch, int n0, int S,
         if (threadIdx.x == 0) refill(false);
       }
       __syncwarp();
-      pair_sync(pair);
-      const int tlo = COI ? sm.coi[s].x : 0, thi = COI ? sm.coi[s].y : kNF;
-      const int t0 = lane + 256 * h;
-      float *orow = power + ((int64_t)b * S + s) * (int64_t)n0 + t0;
-      // e = even-bin transform, g = odd-bin transform, both at u = t0 + 32 p (.x) and u + 512 (.y), w = w2048^u as
-      // (c, -s | s, c) for the two halves (w2048^(u+512) = i w2048^u):  x[u] = e + w g,  x[u + 1024] = e - w g = 2 e - x[u].
-      // The twiddle rides in the additions (the receiving side applies it: both warps do the same work), and each
-      // position leaves as four whole lines.
-      auto finish = [&](const int p, const float2 er, const float2 ei, const float2 gr, const float2 gi, const float4 w) {
-        const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
-        const float2 lr = fma2(gr, wa, fma2(gi, neg2(wb), er)), li = fma2(gi, wa, fma2(gr, wb, ei));
-        float2 lo = fma2(lr, lr, mul2(li, li));      // |x[u]|^2, |x[u + 512]|^2
-        const int ta = t0 + 32 * p;
-        if (COI) {
-          if (ta < tlo || ta > thi) lo.x = NAN;
-          if (ta + 512 < tlo || ta + 512 > thi) lo.y = NAN;
-        }
-        __stcs(orow + 32 * p, lo.x);                 // n0 > 1024: the first half is always inside the row
-        __stcs(orow + 32 * p + 512, lo.y);
-        if (kN + 256 * h + 32 * p < n0) {            // warp-uniform: some lane still has a sample in the second half
-          const float2 hr = fma2(er, bc(2.0f), neg2(lr)), hi = fma2(ei, bc(2.0f), neg2(li));
-          float2 hp = fma2(hr, hr, mul2(hi, hi));    // |x[u + 1024]|^2, |x[u + 1536]|^2
+      group_sync<D>(group);
+      if constexpr (D == 2) {
+        const int t0 = lane + 256 * h;
+        float *orow = orow0 + 256 * h;
+        // e = even-bin transform, g = odd-bin transform, both at u = t0 + 32 p (.x) and u + 512 (.y), w = w2048^u as
+        // (Re | Im) of the two halves (w2048^(u+512) = i w2048^u):  x[u] = e + w g,  x[u + 1024] = e - w g = 2 e - x[u].
+        // The twiddle rides in the additions (the receiving side applies it: both warps do the same work), and each
+        // position leaves as four whole lines.
+        auto finish = [&](const int p, const float2 er, const float2 ei, const float2 gr, const float2 gi, const float4 w) {
+          const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
+          const float2 lr = fma2(gr, wa, fma2(gi, neg2(wb), er)), li = fma2(gi, wa, fma2(gr, wb, ei));
+          float2 lo = fma2(lr, lr, mul2(li, li));      // |x[u]|^2, |x[u + 512]|^2
+          const int ta = t0 + 32 * p;
           if (COI) {
-            if (ta + 1024 < tlo || ta + 1024 > thi) hp.x = NAN;
-            if (ta + 1536 < tlo || ta + 1536 > thi) hp.y = NAN;
+            if (ta < tlo || ta > thi) lo.x = NAN;
+            if (ta + 512 < tlo || ta + 512 > thi) lo.y = NAN;
           }
-          if (ta + 1024 < n0) __stcs(orow + 32 * p + 1024, hp.x);
-          if (ta + 1536 < n0) __stcs(orow + 32 * p + 1536, hp.y);
+          __stcs(orow + 32 * p, lo.x);                 // n0 > 1024: the first half is always inside the row
+          __stcs(orow + 32 * p + 512, lo.y);
+          if (kN + 256 * h + 32 * p < n0) {            // warp-uniform: some lane still has a sample in the second half
+            const float2 hr = fma2(er, bc(2.0f), neg2(lr)), hi = fma2(ei, bc(2.0f), neg2(li));
+            float2 hp = fma2(hr, hr, mul2(hi, hi));    // |x[u + 1024]|^2, |x[u + 1536]|^2
+            if (COI) {
+              if (ta + 1024 < tlo || ta + 1024 > thi) hp.x = NAN;
+              if (ta + 1536 < tlo || ta + 1536 > thi) hp.y = NAN;
+            }
+            if (ta + 1024 < n0) __stcs(orow + 32 * p + 1024, hp.x);
+            if (ta + 1536 < n0) __stcs(orow + 32 * p + 1536, hp.y);
+          }
+        };
+        if (h) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            finish(p, my_mr[p * 32 + lane], my_mi[p * 32 + lane], R[p + 8], I[p + 8], sm.tw_o[0][p + 8][lane]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) finish(p, R[p], I[p], my_mr[p * 32 + lane], my_mi[p * 32 + lane], sm.tw_o[0][p][lane]);
         }
-      };
-      if (h) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p)
-          finish(p, my_mr[p * 32 + lane], my_mi[p * 32 + lane], R[p + 8], I[p + 8], sm.tw_o[p + 8][lane]);
       } else {
+        // radix-4 butterfly of the twiddled transforms t_r = w4096^(r u) G_r at u = lane + 32 (4 h + q) (.x), u + 512 (.y):
+        //   a0 = t0 + t2, a1 = t0 - t2, a2 = t1 + t3, a3 = t1 - t3;  x_0 = a0 + a2, x_2 = a0 - a2, x_1 = a1 + i a3, x_3 = a1 - i a3,
+        // x_q = x[u + 1024 q]; the twiddles of t2 and t3 ride in the additions.
+        const int t0 = lane + 128 * h;
+        float *orow = orow0 + 128 * h;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) finish(p, R[p], I[p], my_mr[p * 32 + lane], my_mi[p * 32 + lane], sm.tw_o[p][lane]);
+        for (int q = 0; q < 4; ++q) {
+          const float2 g0r = my_mr[(0 * 4 + q) * 32 + lane], g0i = my_mi[(0 * 4 + q) * 32 + lane];
+          const float2 g1r = my_mr[(1 * 4 + q) * 32 + lane], g1i = my_mi[(1 * 4 + q) * 32 + lane];
+          const float2 g2r = my_mr[(2 * 4 + q) * 32 + lane], g2i = my_mi[(2 * 4 + q) * 32 + lane];
+          const float2 g3r = my_mr[(3 * 4 + q) * 32 + lane], g3i = my_mi[(3 * 4 + q) * 32 + lane];
+          const float4 w1 = sm.tw_o[0][4 * h + q][lane], w2 = sm.tw_o[1][4 * h + q][lane], w3 = sm.tw_o[2][4 * h + q][lane];
+          const float2 c1 = make_float2(w1.x, w1.y), s1 = make_float2(w1.z, w1.w);
+          const float2 c2 = make_float2(w2.x, w2.y), s2 = make_float2(w2.z, w2.w);
+          const float2 c3 = make_float2(w3.x, w3.y), s3 = make_float2(w3.z, w3.w);
+          const float2 a0r = fma2(g2r, c2, fma2(g2i, neg2(s2), g0r)), a0i = fma2(g2i, c2, fma2(g2r, s2, g0i));
+          const float2 a1r = fma2(g0r, bc(2.0f), neg2(a0r)), a1i = fma2(g0i, bc(2.0f), neg2(a0i));
+          const float2 t1r = fma2(g1i, neg2(s1), mul2(g1r, c1)), t1i = fma2(g1r, s1, mul2(g1i, c1));
+          const float2 a2r = fma2(g3r, c3, fma2(g3i, neg2(s3), t1r)), a2i = fma2(g3i, c3, fma2(g3r, s3, t1i));
+          const float2 a3r = fma2(t1r, bc(2.0f), neg2(a2r)), a3i = fma2(t1i, bc(2.0f), neg2(a2i));
+          const int ta = t0 + 32 * q;
+          float *o = orow + 32 * q;
+          auto put = [&](const int qq, const float2 xr, const float2 xi) {
+            float2 pw = fma2(xr, xr, mul2(xi, xi));    // |x[u + 1024 qq]|^2, |x[u + 512 + 1024 qq]|^2
+            const int tq = ta + kN * qq;
+            if (COI) {
+              if (tq < tlo || tq > thi) pw.x = NAN;
+              if (tq + 512 < tlo || tq + 512 > thi) pw.y = NAN;
+            }
+            if (qq < 2) {                              // n0 > 2048: the first half is always inside the row
+              __stcs(o + kN * qq, pw.x);
+              __stcs(o + kN * qq + 512, pw.y);
+            } else {
+              if (tq < n0) __stcs(o + kN * qq, pw.x);
+              if (tq + 512 < n0) __stcs(o + kN * qq + 512, pw.y);
+            }
+          };
+          put(0, add2(a0r, a2r), add2(a0i, a2i));
+          put(1, fma2(a3i, bc(-1.0f), a1r), add2(a1i, a3r));
+          if (2 * kN + 128 * h + 32 * q < n0)          // warp-uniform, as in the pair kernel
+            put(2, fma2(a2r, bc(-1.0f), a0r), fma2(a2i, bc(-1.0f), a0i));
+          if (3 * kN + 128 * h + 32 * q < n0)
+            put(3, add2(a1r, a3i), fma2(a3r, bc(-1.0f), a1i));
+        }
       }
     }
     if (leader) mbar_arrive(&sm.done[slot]);
@@ -760,20 +837,24 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 }
 
 
-// true: cwt_pair2048_try runs this shape and wants the forward spectra in its layout (CtaSmemP::xh; written by
-// k_fwd_fft_pair2048 in cwt.cu).  The kernel stores the first 1024 samples of a row unconditionally (n0 > 1024).
-// The rows of a series are split over CTAs when the batch is small, but this path also pays for the separate
-// forward-FFT launch: 0.040 ms for 12 series against 0.021 ms + 1.7 us per series for the generic kernel.
-bool cwt_pair2048_covers(int64_t batch, int n0, int nfft, int S, double f0) {
-  return nfft == 2 * kN && f0 >= kZCut && S <= kMaxRowsF && batch >= min_fast_batch(kMinBatchF) && n0 > kN;
+// true: cwt_dif_try runs this shape and wants the forward spectra in its group layout (CtaSmemP::xh; written by
+// k_fwd_fft_pair2048 / k_dif_layout4096 in cwt.cu).  The kernels store the first half of a row unconditionally
+// (n0 > nfft / 2).  The rows of a series are split over CTAs when the batch is small, but this path also pays for
+// the separate forward-FFT launch: 0.040 ms for 12 series of 1346 samples against 0.021 ms + 1.7 us per series
+// for the generic kernel.
+bool cwt_dif_covers(int64_t batch, int n0, int nfft, int S, double f0) {
+  return (nfft == 2 * kN || nfft == 4 * kN) && f0 >= kZCut && S <= kMaxRowsF && batch >= min_fast_batch(kMinBatchF) &&
+         n0 > nfft / 2;
 }
 
-// FP32 CWT + power rows for nfft = 2048 from forward spectra in pair layout (cwt.cu tries this after its
-// forward-FFT kernel).  Returns 1 when the shape is not covered.
-int cwt_pair2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, double dt, const Axes &ax, double f0,
-                     int flags, float *d_power, cudaStream_t st) {
+// FP32 CWT + power rows for nfft = 2048 / 4096 from forward spectra in group layout (`d_layout`: per series
+// `stride` float2 apart, 8 KB / 16 KB each; cwt.cu tries this after its forward-FFT kernel).  Returns 1 when the
+// shape is not covered.
+int cwt_dif_try(const float2 *d_layout, int64_t stride, int64_t batch, int n0, int nfft, double dt, const Axes &ax,
+                double f0, int flags, float *d_power, cudaStream_t st) {
   const int S = ax.J + 1;
-  if (!cwt_pair2048_covers(batch, n0, nfft, S, f0)) return 1;
+  if (!cwt_dif_covers(batch, n0, nfft, S, f0)) return 1;
+  const int D = nfft / kN;
   const bool coi = flags & WTB_COI_MASK;
   std::vector<RowParam> rows(S);
   for (int s = 0; s < S; ++s) {
@@ -783,8 +864,8 @@ int cwt_pair2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, doub
     RowParam &r = rows[s];
     r.a = (float)a;
     r.lognorm = (float)std::log2(std::sqrt(2.0 * kPi * ax.scales[s] / dt) * 0.75112554446494248286 / nfft);
-    // a warp transforms the bins of one parity, j = k / 2 <= jhi < 512
-    const int jhi = khi / 2;
+    // a warp transforms the bins of one residue mod D, j = k / D <= jhi < 512
+    const int jhi = khi / D;
     r.multi = jhi >= 32;
     r.L = r.multi ? std::max(1, std::min(4, ilog2(jhi / 32 + 1))) : std::max(1, ilog2(jhi + 1));
   }
@@ -805,13 +886,14 @@ int cwt_pair2048_try(const float2 *d_xhat, int64_t batch, int n0, int nfft, doub
   const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), (int64_t)sm_count() / batch));
   const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
   WTB_REQUIRE(batch * split < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
-  auto run = [&](auto kern) -> int {
-    WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmemP)));
-    kern<<<grid, kPairWarps * 32, sizeof(CtaSmemP), st>>>(d_xhat, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
+  auto run = [&](auto kern, size_t smem) -> int {
+    WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kDifWarps * 32, smem, st>>>(d_layout, stride, batch, n0, S, d_rows, d_coi, (float)f0, d_power, split);
     WTB_LAUNCH_CHECK();
     return WTB_OK;
   };
-  return coi ? run(k_cwt_pair_2048<true>) : run(k_cwt_pair_2048<false>);
+  if (D == 2) return coi ? run(k_cwt_dif<2, true>, sizeof(CtaSmemP<2>)) : run(k_cwt_dif<2, false>, sizeof(CtaSmemP<2>));
+  return coi ? run(k_cwt_dif<4, true>, sizeof(CtaSmemP<4>)) : run(k_cwt_dif<4, false>, sizeof(CtaSmemP<4>));
 }
 
 }  // namespace wtb

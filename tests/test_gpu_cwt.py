@@ -282,7 +282,7 @@ def test_cwt_fp32_nfft2048_interleaved_passes(shim, monkeypatch, n0, dj, J):
 @pytest.mark.parametrize("n0,dj,J,batch", [(3351, 1 / 8, 65, 300), (4096, 1 / 12, 100, 150), (2049, 1 / 4, -1, 12),
                                             (3000, 1 / 6, 40, 450)])
 def test_cwt_fp32_nfft4096_warp_quads(shim, monkeypatch, n0, dj, J, batch):
-    """Batches (>= 12) of 2049..4096-sample series take the four-warps-per-row kernel (bins k = 4 j + r per
+    """Batches (at least four series per SM by default; the tests lower the threshold to 1) of 2049..4096-sample series take the four-warps-per-row kernel (bins k = 4 j + r per
     warp, radix-4 combine through the transpose buffers).  Oracle parity on sampled series, generic-kernel
     parity on all; 300 and 450 series give every CTA two to four series (its two-slot spectrum ring is
     refilled), 12 series split their rows over CTAs."""
@@ -301,7 +301,7 @@ def test_cwt_fp32_nfft4096_warp_quads(shim, monkeypatch, n0, dj, J, batch):
     # a series' numbers do not depend on the batch it came in (split over CTAs or not)
     first, _ = shim.cwt_morlet(x[:13], DT, dj, 2 * DT, J, f64=False)
     assert np.array_equal(first, power[:13])
-    # below the default threshold (12 series) the register-row kernel (k_cwt_rows_4096) serves the call
+    # below the default threshold (four series per SM) the register-row kernel (k_cwt_rows_4096) serves the call
     monkeypatch.delenv("WTB_CWT_MIN_BATCH")
     small, _ = shim.cwt_morlet(x[:5], DT, dj, 2 * DT, J, f64=False)
     assert not np.array_equal(small, power[:5])

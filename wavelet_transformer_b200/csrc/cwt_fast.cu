@@ -841,10 +841,13 @@ int cwt_fast_try(const float *d_x, int64_t batch, int n0, int nfft, double dt, c
 // k_fwd_fft_pair2048 / k_dif_layout4096 in cwt.cu).  The kernels store the first half of a row unconditionally
 // (n0 > nfft / 2).  The rows of a series are split over CTAs when the batch is small, but this path also pays for
 // the separate forward-FFT launch: 0.040 ms for 12 series of 1346 samples against 0.021 ms + 1.7 us per series
-// for the generic kernel.
+// for the generic kernel (nfft = 2048 starts at 12 series).
 bool cwt_dif_covers(int64_t batch, int n0, int nfft, int S, double f0) {
-  return (nfft == 2 * kN || nfft == 4 * kN) && f0 >= kZCut && S <= kMaxRowsF && batch >= min_fast_batch(kMinBatchF) &&
-         n0 > nfft / 2;
+  // nfft = 4096: the register rows of wct_fast.cu (one CTA per two series and scale: finer work items) are faster or
+  // equal up to a few series per SM -- 0.037 / 0.064 / 0.110 / 0.185 / 0.286 ms for 12 / 64 / 148 / 300 / 500 series
+  // against 0.061 / 0.075 / 0.107 / 0.194 / 0.281 ms here; 1000 series: 0.532 against 0.505 ms, 4000: 2.04 against 1.87
+  const int64_t min_batch = min_fast_batch(nfft == 2 * kN ? kMinBatchF : 4 * (int64_t)sm_count());
+  return (nfft == 2 * kN || nfft == 4 * kN) && f0 >= kZCut && S <= kMaxRowsF && batch >= min_batch && n0 > nfft / 2;
 }
 
 // FP32 CWT + power rows for nfft = 2048 / 4096 from forward spectra in group layout (`d_layout`: per series
@@ -882,9 +885,20 @@ int cwt_dif_try(const float2 *d_layout, int64_t stride, int64_t batch, int n0, i
     d_coi = (ushort2 *)(d_rows + kMaxRowsF);
     WTB_CUDA(cudaMemcpyAsync(d_coi, rng.data(), sizeof(ushort2) * S, cudaMemcpyHostToDevice, st));
   }
-  // fewer series than SMs: the rows of a series are dealt to up to 16 CTAs
-  const int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), (int64_t)sm_count() / batch));
-  const int grid = (int)std::min<int64_t>(batch * split, (int64_t)sm_count());
+  // Fewer series than SMs: the rows of a series are dealt to up to 16 CTAs.  A few series per SM: CTAs take whole
+  // items, so the last wave is only as full as ceil() leaves it (500 series on 148 SMs: 3.4 -> 4 rounds, 84 %);
+  // dealing each series' rows to 2 .. 4 items evens that out (the X^ reload per item is 8 / 16 KB).
+  const int64_t sms = sm_count();
+  int split = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, S), sms / batch));
+  if (batch >= sms && batch < 16 * sms) {
+    double best = 0.0;
+    for (int c = 1; c <= std::min(4, S); ++c) {
+      const double waves = (double)(batch * c) / (double)sms;
+      const double eff = waves / std::ceil(waves) * (1.0 - 0.01 * (c - 1));
+      if (eff > best + 1e-9) { best = eff; split = c; }
+    }
+  }
+  const int grid = (int)std::min<int64_t>(batch * split, sms);
   WTB_REQUIRE(batch * split < (1LL << 31), WTB_EUNSUPPORTED, "batch too large for one launch");
   auto run = [&](auto kern, size_t smem) -> int {
     WTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -610,6 +610,44 @@ def bench_filterbank(c):
                       "algorithmic bytes 8 N (1 + J+1) per series"}
 
 
+def bench_cwt_shapes(c):
+    """Fused CWT+power at the other FFT lengths (rank-local, device-resident): BASELINE cfg1's shape in batch
+    (1346 samples -> nfft 2048, 85 scales: two warps per row) and the Monte-Carlo surrogate length as a plain
+    CWT (3351 -> 4096, 66 scales: four warps per row).  Roofline = the slower of FFT flops at the nominal FP32
+    peak and coefficient bytes at the measured HBM bandwidth (north_star); SURVEY 8d's per-series figures."""
+    torch, shim = c.torch, c.shim
+    fp32_peak = 148 * 128 * 2 * 1.965e9
+    out = []
+    for label, n0, dj, J, batch in (("cfg1 shape", 1346, 1 / 12, 84, 10_000), ("nfft 4096", 3351, 1 / 8, 65, 4_000)):
+        S = J + 1
+        x = torch.randn((batch, n0), dtype=torch.float32, device=c.dev)
+        pw = torch.empty((batch, S, n0), dtype=torch.float32, device=c.dev)
+
+        def step():
+            shim.cwt_power_device(x.data_ptr(), batch, n0, DT, dj, 2 * DT, J, 6.0, pw.data_ptr(), f64=False)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / 5
+        nfft = 1 << (n0 - 1).bit_length()
+        lg = nfft.bit_length() - 1
+        flop = 5.0 * nfft * lg + S * (5.0 * nfft * lg + 5.0 * nfft)
+        by = 4.0 * n0 * (1 + S)
+        t_hbm, t_fp32 = by / (c.hbm_peak * 1e9), flop / fp32_peak
+        out.append({"shape": label, "n0": n0, "nfft": nfft, "scales": S, "series": batch, "ms": t * 1e3,
+                    "value": batch * S * n0 / t, "unit": "coeff/s", "per_gpu": True,
+                    "achieved_GBs": by * batch / t / 1e9, "achieved_TFLOPs": flop * batch / t / 1e12,
+                    "bound": "fp32" if t_fp32 > t_hbm else "hbm", "frac_roofline": max(t_hbm, t_fp32) * batch / t})
+        del x, pw
+    return out
+
+
 def run_gpu(args):
     c = setup_gpu(args)
     sampler = ClockSampler(c.local) if c.rank == 0 else None
@@ -628,6 +666,7 @@ def run_gpu(args):
             line["secondary"] = guarded("cfg4 secondary", lambda: bench_cwt(c, args, sampler2, steps=args.secondary_steps,
                                                                            warmup=3))
             line["secondary_filterbank"] = guarded("filterbank secondary", lambda: bench_filterbank(c))
+            line["secondary_cwt_shapes"] = guarded("cwt shapes secondary", lambda: bench_cwt_shapes(c))
     else:
         line = bench_cwt(c, args, sampler)
         if not args.no_secondary:
